@@ -1,0 +1,52 @@
+/* api_common.h -- shared state of the C-ABI layer (error channel, launch counter, scene object). */
+#ifndef IMBA_API_COMMON_H
+#define IMBA_API_COMMON_H
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <string>
+#include <vector>
+#include <cuda_runtime.h>
+#include "../../include/imba_b200.h"
+#include "bvh8_build.h"
+#include "kernels.h"
+
+void imba_set_error(const char* fmt, ...);
+extern std::atomic<uint64_t> g_imba_launches;
+
+#define IMBA_CUDA(expr, ret)                                                                         \
+    do { cudaError_t e__ = (expr);                                                                   \
+         if (e__ != cudaSuccess) { imba_set_error("%s:%d %s: %s", __FILE__, __LINE__, #expr, cudaGetErrorString(e__)); return ret; } \
+    } while (0)
+
+struct DeviceShading; // shade.cu
+
+struct imba_scene {
+    int       device = 0;
+    int       sm_count = 0;
+    // acceleration structure
+    uint4*    d_nodes = nullptr; float4* d_tris = nullptr; float4* d_insts = nullptr;
+    uint32_t  top_root = 0;
+    int64_t   stats[5] = { 0, 0, 0, 0, 0 };
+    // opacity masks
+    bool      has_masks = false; bool owns_masks = true;
+    int*      d_mask_indices = nullptr; float2* d_mask_texcoords = nullptr; int* d_masks = nullptr; uint8_t* d_mask_buffer = nullptr;
+    // work counters (one per in-flight launch)
+    unsigned* d_counters = nullptr; std::atomic<unsigned> next_counter{ 0 };
+    static constexpr unsigned kCounters = 4096;
+    // staging for host-buffer traversal
+    static constexpr int kChunkRays = 1 << 20;
+    float4*   d_stage_rays[2] = { nullptr, nullptr }; int4* d_stage_hits[2] = { nullptr, nullptr };
+    cudaStream_t stage_stream[2] = { nullptr, nullptr };
+    // shading data (geometry, materials, lights, textures), null until uploaded
+    DeviceShading* shading = nullptr;
+    int grid_cache[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
+};
+
+/* Uploads a converted structure; fills scene->d_nodes etc. */
+int imba_scene_upload_accel(imba_scene* s, const Bvh8& b);
+/* Launches traversal on device buffers. */
+int imba_scene_trace(imba_scene* s, const imba_ray* d_rays, imba_hit* d_hits, int count, int any_hit, uint32_t* d_counters,
+                     cudaStream_t stream);
+
+#endif

@@ -1,0 +1,30 @@
+/* kernels.h -- internal launch interface between the C-ABI layer (api.cu) and the CUDA kernels. */
+#ifndef IMBA_KERNELS_H
+#define IMBA_KERNELS_H
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define IMBA_TRAVERSAL_STACK 40 /* 8-byte entries per ray; scenes needing more are rejected at upload */
+
+struct TraceArgs {
+    const uint4*   nodes;      // Node8[] as 5 x uint4
+    const float4*  tris;       // Tri48[] as 3 x float4
+    const float4*  insts;      // Inst64[] as 4 x float4
+    uint32_t       top_root;
+    const float4*  rays;       // imba_ray[] as 2 x float4
+    int4*          hits;       // imba_hit[]
+    int            count;
+    unsigned*      counter;    // work counter, zero at launch
+    uint32_t*      stats;      // 4 x u32 per ray or null
+    // opacity masks (core/mask.h), only read by the MASKS instantiations
+    const int*     indices;    // 4 ints per global triangle
+    const float2*  texcoords;
+    const int*     masks;      // 3 ints per material
+    const uint8_t* mask_buffer;
+};
+
+int         imba_trace_block_threads();
+int         imba_trace_blocks_per_sm(bool any_hit, bool masks, bool stats);
+cudaError_t imba_launch_trace(const TraceArgs& a, bool any_hit, bool masks, bool stats, int grid, cudaStream_t s);
+
+#endif

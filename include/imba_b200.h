@@ -1,0 +1,218 @@
+/* imba_b200.h -- C ABI of the B200-native hot path of imbatracer.
+ *
+ * Plain C, plain pointers and sizes, no torch / CUDA types in any signature (streams are
+ * passed as void*).  All functions are exported from libimba_b200.so.
+ *
+ * Citations are relative to the reference tree (microcompunics/imbatracer).
+ *
+ * Level 1 (L1) is a symbol-for-symbol replacement of the four entry points the reference
+ * binds from the external AnyDSL/traversal library (core/traversal_interface.h:4-10, call
+ * sites render/scheduling/ray_queue.h:254-265, 279-290, 304-315, 329-340).
+ * Level 2 (L2) is the device-resident API behind the reference's RayQueue / RayScheduler /
+ * Integrator plug-in points (ray_scheduler.h:15-38, integrator.h:19-39): the scene is
+ * flattened once, queues live in HBM, a whole progressive iteration runs without leaving
+ * the device.
+ *
+ * Error model: the reference's entry points return void and have no error channel
+ * (ray_queue.h:248,270-271 only assert).  L1 keeps that signature; failures (no CUDA device,
+ * launch error) are fatal: message on stderr + abort().  There is NO CPU fallback.
+ * L2 functions return 0 on success or a negative imba_status; imba_last_error() gives text.
+ */
+#ifndef IMBA_B200_H
+#define IMBA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------------------------------
+ * ABI data types (what the AnyDSL-generated traversal_{cpu,gpu}.h declare)
+ * ---------------------------------------------------------------------------------------- */
+typedef struct { float x, y, z, w; } imba_vec4;
+typedef struct { float x, y; } imba_vec2;
+/* org.w = tmin, dir.w = tmax (render/ray_gen/camera.h:61-64) */
+typedef struct { imba_vec4 org; imba_vec4 dir; } imba_ray;
+/* tri_id < 0 = miss (integrator.h:57); tmax = t along the un-normalised dir; u = weight of v1 (integrator.h:90-101) */
+typedef struct { int32_t tri_id; int32_t inst_id; float tmax; float u; } imba_hit;
+/* MBVH4 node of the CPU layout (core/cpu_adapter.cpp:14-25, 80-100) */
+typedef struct { float min_x[4], min_y[4], min_z[4], max_x[4], max_y[4], max_z[4]; int32_t children[4]; } imba_node4;
+/* BVH2 node of the GPU layout (core/gpu_adapter.cpp:14-31, 79-98) */
+typedef struct { float lo_x, lo_y, lo_z, hi_x, hi_y, hi_z; } imba_bbox;
+typedef struct { imba_bbox left_bb, right_bb; int32_t left, right; } imba_node2;
+/* core/cpu_adapter.cpp:356-365 */
+typedef struct { float transf[3][4]; int32_t id; int32_t next; int32_t pad[2]; } imba_instance_node;
+/* core/mask.h:9-20 */
+typedef struct { int32_t width, height, offset; } imba_mask;
+
+typedef enum {
+    IMBA_OK = 0,
+    IMBA_ERR_NO_DEVICE = -1,
+    IMBA_ERR_CUDA = -2,
+    IMBA_ERR_INVALID = -3,
+    IMBA_ERR_OVERFLOW = -4
+} imba_status;
+
+const char* imba_last_error(void);
+/* Returns the number of CUDA kernels this library has launched since load (bench.py "gpu_launches"). */
+uint64_t imba_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * L1: drop-in traversal entry points
+ * ---------------------------------------------------------------------------------------- */
+/* Replaces traversal_gpu::intersect_gpu_masked_instanced / occluded_gpu_masked_instanced
+ * (ray_queue.h:279-290, 329-340).  Every pointer is a DEVICE pointer on the current CUDA
+ * device (the reference allocates them with anydsl::Array(Platform::Cuda, Device(0)),
+ * ray_queue.h:78-79, scene.cpp:14-26).  nodes/tris are in the reference's BVH2 GPU layout.
+ * Synchronous: hits are complete on return (the caller D2H-copies them right away,
+ * ray_queue.h:292).  Re-entrant for disjoint ray/hit buffers (tile_scheduler.h:69-78).
+ * count may include padding rays (ray_queue.h:273); they are traced like any other ray.
+ * The compressed 8-wide BVH is built on first use per (nodes, tris, instances, root) and cached. */
+#ifndef IMBA_B200_NO_L1_DECLS
+void intersect_gpu_masked_instanced(int root, imba_node2* nodes, imba_instance_node* instances, imba_vec4* tris,
+                                    imba_ray* rays, imba_hit* hits, int* indices, imba_vec2* texcoords,
+                                    imba_mask* masks, char* mask_buffer, int count);
+void occluded_gpu_masked_instanced(int root, imba_node2* nodes, imba_instance_node* instances, imba_vec4* tris,
+                                   imba_ray* rays, imba_hit* hits, int* indices, imba_vec2* texcoords,
+                                   imba_mask* masks, char* mask_buffer, int count);
+/* Replaces traversal_cpu::intersect_cpu_masked_instanced / occluded_cpu_masked_instanced
+ * (ray_queue.h:254-265, 304-315).  Every pointer is a HOST pointer; nodes/tris are in the
+ * reference's MBVH4 CPU layout.  Rays are staged through pinned memory in chunks and copied,
+ * traced and copied back on two streams so that PCIe and the SMs overlap.  Lets an unmodified
+ * `--cpu` build of the reference run its traversal on the B200 by swapping the library. */
+void intersect_cpu_masked_instanced(int root, imba_node4* nodes, imba_instance_node* instances, imba_vec4* tris,
+                                    imba_ray* rays, imba_hit* hits, int* indices, imba_vec2* texcoords,
+                                    imba_mask* masks, char* mask_buffer, int count);
+void occluded_cpu_masked_instanced(int root, imba_node4* nodes, imba_instance_node* instances, imba_vec4* tris,
+                                   imba_ray* rays, imba_hit* hits, int* indices, imba_vec2* texcoords,
+                                   imba_mask* masks, char* mask_buffer, int count);
+#endif /* IMBA_B200_NO_L1_DECLS */
+/* Drops every cached acceleration structure built by the L1 entry points (call after the host
+ * rebuilt or freed its node arrays, e.g. Scene::build_top_level_accel, scene.cpp:114). */
+void imba_l1_invalidate(void);
+
+/* ------------------------------------------------------------------------------------------
+ * L2: flattened scene (what render/scene.h keeps host-side for shading)
+ * ---------------------------------------------------------------------------------------- */
+typedef enum { IMBA_ACCEL_MBVH4 = 0, IMBA_ACCEL_BVH2 = 1 } imba_accel_layout;
+typedef enum { IMBA_MAT_DIFFUSE = 0, IMBA_MAT_MIRROR = 1, IMBA_MAT_GLASS = 2, IMBA_MAT_GLOSSY = 3 } imba_material_kind;
+typedef enum { IMBA_LIGHT_TRIANGLE = 0, IMBA_LIGHT_DIRECTIONAL = 1, IMBA_LIGHT_POINT = 2, IMBA_LIGHT_SPOT = 3,
+               IMBA_LIGHT_ENV = 4 } imba_light_kind;
+
+/* render/materials/materials.h:58-191 flattened to one tagged record (64 bytes). */
+typedef struct {
+    int32_t kind;          /* imba_material_kind */
+    int32_t diffuse_tex;   /* texture index or -1 (DiffuseMaterial::sampler_, GlossyMaterial::diff_sampler_) */
+    int32_t bump_tex;      /* texture index or -1 (Material::bump_) */
+    int32_t is_emitter;    /* Material::emit_ != nullptr */
+    float kd[3];           /* DiffuseMaterial::color_ / GlossyMaterial::diffuse_color_ */
+    float eta;             /* MirrorMaterial fresnel eta / GlassMaterial::eta_ */
+    float ks[3];           /* MirrorMaterial::scale_ / GlassMaterial::reflectance_ / GlossyMaterial::specular_color_ */
+    float kappa;           /* MirrorMaterial fresnel kappa */
+    float tf[3];           /* GlassMaterial::transmittance_ */
+    float exponent;        /* GlossyMaterial::exponent_ */
+    float emit[3];         /* AreaEmitter::intensity (light.h:14-47) */
+    float emit_area;       /* AreaEmitter::area */
+} imba_material;
+
+/* render/light.h flattened (80 bytes). */
+typedef struct {
+    int32_t kind;          /* imba_light_kind */
+    float   angle;         /* SpotLight::angle_ (radians) */
+    float   pad0[2];
+    float   intensity[4];  /* rgb (+pad) */
+    float   p0[4];         /* triangle v0 / position / direction(dir light) */
+    float   p1[4];         /* triangle v1 / spot direction */
+    float   p2[4];         /* triangle v2 */
+} imba_light;
+
+typedef struct { int32_t mesh_id; float mat[12]; float inv_mat[12]; } imba_instance; /* core/mesh.h:20-27 (3x4 row-major) */
+typedef struct { int32_t width, height; int64_t offset; } imba_texture; /* offset in float4 texels into the texel pool */
+
+typedef struct {
+    /* geometry of all meshes, concatenated in mesh order (render/scene.cpp:74-97) */
+    int32_t        mesh_count;
+    const int32_t* mesh_vertex_base;  /* [mesh_count + 1] */
+    const int32_t* mesh_tri_base;     /* [mesh_count + 1]  == Scene::tri_layout_ */
+    const float*   vertices;          /* 4 floats per vertex (core/mesh.h:66) */
+    const float*   normals;           /* 4 floats per vertex (FLOAT3 attribute stride 16, mesh.h:128) */
+    const float*   texcoords;         /* 2 floats per vertex */
+    const float*   geom_normals;      /* 4 floats per triangle */
+    const int32_t* indices;           /* 4 ints per triangle: mesh-local i0,i1,i2, material id */
+    int32_t        instance_count;
+    const imba_instance* instances;
+    int32_t        material_count;
+    const imba_material* materials;
+    int32_t        light_count;
+    const imba_light* lights;
+    int32_t        texture_count;
+    const imba_texture* textures;
+    const float*   texels;            /* float4 RGBA pool */
+    int64_t        texel_count;
+    /* environment map (render/light.h:361-485); env_tex = -1 if none */
+    int32_t        env_tex;
+    float          env_intensity;
+    /* scene bounding sphere (render/scene.cpp:190-202) */
+    float          bsphere_center[3];
+    float          bsphere_radius;
+    /* acceleration structure in one of the reference's layouts (core/{cpu,gpu}_adapter.cpp) */
+    int32_t        accel_layout;      /* imba_accel_layout */
+    int32_t        root;
+    const void*    nodes;             /* imba_node4[] or imba_node2[] */
+    int32_t        node_count;
+    const imba_vec4* tris;
+    int64_t        tri_vec4_count;
+    const imba_instance_node* inst_nodes;
+    int32_t        inst_node_count;
+    /* opacity masks (core/mask.h), optional: mask_count == 0 -> everything opaque */
+    int32_t        mask_count;
+    const imba_mask* masks;
+    const uint8_t* mask_buffer;
+    int64_t        mask_buffer_size;
+    /* global per-triangle index records used by the mask test: 4 ints per global triangle with
+     * texcoord indices offset per mesh (scene.cpp:89-93); may be NULL when mask_count == 0 */
+    const int32_t* mask_indices;
+    const imba_vec2* mask_texcoords;
+    int64_t        mask_texcoord_count;
+} imba_scene_desc;
+
+typedef struct imba_scene imba_scene;
+
+/* Uploads the scene to the current CUDA device and converts the acceleration structure to the
+ * compressed 8-wide layout (replaces Scene::upload_* , scene.cpp:132-188). */
+imba_scene* imba_scene_create(const imba_scene_desc* desc);
+void        imba_scene_destroy(imba_scene* scene);
+/* Statistics of the converted structure: out[0]=bvh8 nodes, [1]=triangles (48-byte blocks), [2]=instances,
+ * [3]=bytes of node+triangle storage, [4]=max depth. */
+int imba_scene_stats(const imba_scene* scene, int64_t out[5]);
+
+/* Closest-hit (any_hit = 0) or occlusion (any_hit = 1) traversal of `count` rays.
+ * d_rays / d_hits are device pointers; asynchronous on `stream` (a cudaStream_t, NULL = default stream).
+ * d_counters (optional, device, 4 uint32 per ray) receives per-ray {nodes fetched, triangle blocks fetched,
+ * instances entered, stack high-water}: the N_node / N_tri of the roofline model. */
+int imba_trace(imba_scene* scene, const imba_ray* d_rays, imba_hit* d_hits, int count, int any_hit,
+               uint32_t* d_counters, void* stream);
+/* Same with HOST buffers: pinned staging, chunked H2D / trace / D2H overlap; synchronous.
+ * This is RayQueue::traverse_gpu / traverse_occluded_gpu (ray_queue.h:269-293, 319-343). */
+int imba_trace_host(imba_scene* scene, const imba_ray* h_rays, imba_hit* h_hits, int count, int any_hit);
+
+/* Page-locks / unlocks a host buffer that is passed to imba_trace_host repeatedly (a RayQueue's ray and hit arrays,
+ * ray_queue.h:78-79) so that the chunked copies overlap with traversal. */
+int imba_host_register(void* ptr, size_t bytes);
+int imba_host_unregister(void* ptr);
+
+/* Host-only conversion of a reference-layout structure to the device layout (no CUDA device needed): the arrays that
+ * imba_scene_create uploads.  Node = 80 bytes, triangle = 48 bytes, instance = 64 bytes (imbatracer_b200/csrc/bvh8.h). */
+typedef struct imba_bvh8 imba_bvh8;
+imba_bvh8* imba_bvh8_build(int accel_layout, int root, const void* nodes, const imba_vec4* tris,
+                           const imba_instance_node* inst_nodes);
+void imba_bvh8_free(imba_bvh8* h);
+int  imba_bvh8_arrays(const imba_bvh8* h, const void** nodes, int64_t* node_count, const void** tris, int64_t* tri_count,
+                      const void** insts, int64_t* inst_count, uint32_t* top_root, int32_t* max_depth);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IMBA_B200_H */

@@ -1,0 +1,413 @@
+/* ORACLE / TEST INFRASTRUCTURE -- never linked into or called by the product path.
+ *
+ * Headless C-API driver around the UNMODIFIED reference host code, compiled in place from
+ * /root/reference/src (see oracle/Makefile) against the shim headers in oracle/shim and the
+ * traversal restatement in oracle/traversal_oracle.cpp.  It replaces frontend/main.cpp +
+ * frontend/render_window.cpp (SDL) and exposes:
+ *   - scene loading (frontend/build_scene.cpp:548) and export of the flattened scene in the
+ *     product's imba_scene_desc form (what a maintainer's binding would fill);
+ *   - full renders through the reference's own TileScheduler + PathTracer / VCMIntegrator;
+ *   - PathTracer::process_primary_rays on an injected batch, via a RayScheduler subclass
+ *     (the reference's own plug-in point, ray_scheduler.h:15-38);
+ *   - RNG known-answer values.
+ * Output lives in oracle/_ref/ (git-ignored, travels to the GPU box).
+ */
+#include <algorithm>
+#include <atomic>
+#include <cfloat>
+#include <chrono>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <fstream>
+#include <functional>
+#include <iostream>
+#include <list>
+#include <memory>
+#include <mutex>
+#include <random>
+#include <sstream>
+#include <string>
+#include <thread>
+#include <unordered_map>
+#include <vector>
+#include <array>
+#include <numeric>
+#include <condition_variable>
+#include <deque>
+
+// Test infrastructure needs to read private parameters of the reference's materials and lights
+// (there are no getters).  Standard headers are all included above, before the keyword hack.
+#define private public
+#define protected public
+#include "imbatracer/frontend/cmd_line.h"
+#include "imbatracer/frontend/build_scene.h"
+#include "imbatracer/loaders/loaders.h"
+#include "imbatracer/render/scene.h"
+#include "imbatracer/render/ray_gen/ray_gen.h"
+#include "imbatracer/render/ray_gen/camera.h"
+#include "imbatracer/render/scheduling/tile_scheduler.h"
+#include "imbatracer/render/integrators/pt.h"
+#include "imbatracer/render/integrators/vcm.h"
+#undef private
+#undef protected
+
+#define IMBA_B200_NO_L1_DECLS /* the shim headers declare the same symbols inside namespaces */
+#include "../include/imba_b200.h"
+
+using namespace imba;
+
+// load_png.cpp needs libpng (absent); the Cornell scenes have no textures.
+namespace imba { bool load_png(const Path&, Image&) { return false; } }
+
+namespace {
+
+struct RefScene {
+    std::unique_ptr<Scene> scene;
+    float3 cam_pos, cam_dir, cam_up;
+    bool gpu_layout;
+    // storage for the exported flat scene
+    std::vector<int32_t> mesh_vertex_base, mesh_tri_base, indices;
+    std::vector<float> vertices, normals, texcoords, geom_normals;
+    std::vector<imba_instance> instances;
+    std::vector<imba_material> materials;
+    std::vector<imba_light> lights;
+    std::vector<imba_texture> textures;
+    std::vector<float> texels;
+    int node_count = 0;
+};
+
+struct Quiet {
+    std::streambuf* old;
+    std::ostringstream sink;
+    Quiet() { old = std::cout.rdbuf(sink.rdbuf()); }
+    ~Quiet() { std::cout.rdbuf(old); }
+};
+
+template <typename Node> int count_nodes(const Node* nodes, int root);
+template <> int count_nodes<traversal_cpu::Node>(const traversal_cpu::Node* nodes, int root) {
+    int maxi = root; std::vector<int> st{ root };
+    while (!st.empty()) { int i = st.back(); st.pop_back(); maxi = std::max(maxi, i);
+        for (int k = 0; k < 4; ++k) { int c = nodes[i].children[k]; if (c == 0) break; if (c > 0) st.push_back(c); } }
+    return maxi + 1;
+}
+template <> int count_nodes<traversal_gpu::Node>(const traversal_gpu::Node* nodes, int root) {
+    int maxi = root; std::vector<int> st{ root };
+    while (!st.empty()) { int i = st.back(); st.pop_back(); maxi = std::max(maxi, i);
+        if (nodes[i].left > 0) st.push_back(nodes[i].left);
+        if (nodes[i].right > 0 && nodes[i].right != 0x76543210) st.push_back(nodes[i].right); }
+    return maxi + 1;
+}
+
+void setup_camera(PerspectiveCamera& cam, const float3& pos, const float3& dir_in, const float3& up_in) {
+    // CameraControl::setup, frontend/main.cpp:64-71
+    float3 up = normalize(normalize(up_in));
+    float3 dir = normalize(normalize(dir_in));
+    float3 right = normalize(cross(dir, up));
+    up = normalize(cross(right, dir));
+    cam.move(pos, dir, up);
+}
+
+/// Scheduler that feeds one injected batch through the integrator's callbacks.
+template <typename State, typename Shadow>
+class BatchScheduler : public RayScheduler<State, Shadow> {
+    using Base = RayScheduler<State, Shadow>;
+public:
+    BatchScheduler(Scene& s) : Base(s, false) {}
+    RayQueue<State>* prim = nullptr; RayQueue<Shadow>* shadow = nullptr;
+    void run_iteration(AtomicImage& out, typename Base::ProcessShadowFn, typename Base::ProcessPrimaryFn process_primary,
+                       typename Base::SamplePixelFn) override {
+        process_primary(*prim, *shadow, out);
+    }
+};
+
+} // namespace
+
+extern "C" {
+
+void* ref_scene_load(const char* path, int gpu_layout) {
+    Quiet q;
+    auto rs = new RefScene;
+    rs->gpu_layout = gpu_layout != 0;
+    rs->scene.reset(new Scene(!rs->gpu_layout, rs->gpu_layout));
+    if (!build_scene(Path(path), *rs->scene, rs->cam_pos, rs->cam_dir, rs->cam_up)) { delete rs; return nullptr; }
+    return rs;
+}
+
+void ref_scene_free(void* h) { delete (RefScene*)h; }
+
+void ref_scene_camera(void* h, float* pos, float* dir, float* up) {
+    auto rs = (RefScene*)h;
+    for (int i = 0; i < 3; ++i) { pos[i] = rs->cam_pos[i]; dir[i] = rs->cam_dir[i]; up[i] = rs->cam_up[i]; }
+}
+
+/// Fills `d` with pointers into storage owned by the handle.
+int ref_scene_export(void* h, imba_scene_desc* d) {
+    auto rs = (RefScene*)h;
+    Scene& sc = *rs->scene;
+    memset(d, 0, sizeof(*d));
+    rs->mesh_vertex_base.assign(1, 0); rs->mesh_tri_base.assign(1, 0);
+    rs->vertices.clear(); rs->normals.clear(); rs->texcoords.clear(); rs->geom_normals.clear(); rs->indices.clear();
+    for (size_t m = 0; m < sc.mesh_count(); ++m) {
+        const Mesh& mesh = sc.mesh(m);
+        auto tc = mesh.attribute<float2>(MeshAttributes::TEXCOORDS);
+        auto nr = mesh.attribute<float3>(MeshAttributes::NORMALS);
+        auto gn = mesh.attribute<float3>(MeshAttributes::GEOM_NORMALS);
+        for (size_t v = 0; v < mesh.vertex_count(); ++v) {
+            const float4& p = mesh.vertices()[v];
+            rs->vertices.insert(rs->vertices.end(), { p.x, p.y, p.z, 1.0f });
+            rs->normals.insert(rs->normals.end(), { nr[v].x, nr[v].y, nr[v].z, 0.0f });
+            rs->texcoords.insert(rs->texcoords.end(), { tc[v].x, tc[v].y });
+        }
+        for (size_t t = 0; t < mesh.triangle_count(); ++t) {
+            rs->geom_normals.insert(rs->geom_normals.end(), { gn[t].x, gn[t].y, gn[t].z, 0.0f });
+            for (int k = 0; k < 4; ++k) rs->indices.push_back((int32_t)mesh.indices()[t * 4 + k]);
+        }
+        rs->mesh_vertex_base.push_back(rs->mesh_vertex_base.back() + (int)mesh.vertex_count());
+        rs->mesh_tri_base.push_back(rs->mesh_tri_base.back() + (int)mesh.triangle_count());
+        if (sc.local_tri_id(0, (int)m) != -rs->mesh_tri_base[m]) return -1;
+    }
+    rs->instances.clear();
+    for (auto& inst : sc.instances()) {
+        imba_instance o; o.mesh_id = inst.id;
+        memcpy(o.mat, &inst.mat, 48); memcpy(o.inv_mat, &inst.inv_mat, 48);
+        rs->instances.push_back(o);
+    }
+    // textures
+    rs->textures.clear(); rs->texels.clear();
+    std::unordered_map<const TextureSampler*, int> tex_id;
+    for (size_t t = 0; t < sc.texture_count(); ++t) {
+        const Image& img = sc.texture(t)->image();
+        imba_texture o; o.width = img.width(); o.height = img.height(); o.offset = (int64_t)rs->texels.size() / 4;
+        for (int i = 0; i < img.width() * img.height(); ++i) { const rgba& p = img.pixels()[i]; rs->texels.insert(rs->texels.end(), { p.x, p.y, p.z, p.w }); }
+        rs->textures.push_back(o); tex_id[sc.texture(t).get()] = (int)t;
+    }
+    auto tid = [&](const TextureSampler* s) { return s ? tex_id.at(s) : -1; };
+    rs->materials.clear();
+    for (size_t m = 0; m < sc.material_count(); ++m) {
+        Material* mat = sc.material(m).get();
+        imba_material o; memset(&o, 0, sizeof(o)); o.diffuse_tex = -1; o.bump_tex = tid(mat->bump_);
+        if (auto p = dynamic_cast<DiffuseMaterial*>(mat)) {
+            o.kind = IMBA_MAT_DIFFUSE; o.diffuse_tex = tid(p->sampler_);
+            if (!p->sampler_) { o.kd[0] = p->color_.x; o.kd[1] = p->color_.y; o.kd[2] = p->color_.z; }
+        } else if (auto p = dynamic_cast<MirrorMaterial*>(mat)) {
+            o.kind = IMBA_MAT_MIRROR; o.eta = p->fresnel_.eta_; o.kappa = p->fresnel_.kappa_;
+            o.ks[0] = p->scale_.x; o.ks[1] = p->scale_.y; o.ks[2] = p->scale_.z;
+        } else if (auto p = dynamic_cast<GlassMaterial*>(mat)) {
+            o.kind = IMBA_MAT_GLASS; o.eta = p->eta_;
+            o.ks[0] = p->reflectance_.x; o.ks[1] = p->reflectance_.y; o.ks[2] = p->reflectance_.z;
+            o.tf[0] = p->transmittance_.x; o.tf[1] = p->transmittance_.y; o.tf[2] = p->transmittance_.z;
+        } else if (auto p = dynamic_cast<GlossyMaterial*>(mat)) {
+            o.kind = IMBA_MAT_GLOSSY; o.exponent = p->exponent_; o.diffuse_tex = tid(p->diff_sampler_);
+            o.ks[0] = p->specular_color_.x; o.ks[1] = p->specular_color_.y; o.ks[2] = p->specular_color_.z;
+            o.kd[0] = p->diffuse_color_.x; o.kd[1] = p->diffuse_color_.y; o.kd[2] = p->diffuse_color_.z;
+        } else return -2;
+        if (auto e = mat->emitter()) {
+            o.is_emitter = 1; o.emit[0] = e->intensity.x; o.emit[1] = e->intensity.y; o.emit[2] = e->intensity.z; o.emit_area = e->area;
+        }
+        rs->materials.push_back(o);
+    }
+    rs->lights.clear();
+    for (size_t l = 0; l < sc.light_count(); ++l) {
+        Light* li = sc.light(l).get();
+        imba_light o; memset(&o, 0, sizeof(o));
+        auto set3 = [](float* d, const float3& v) { d[0] = v.x; d[1] = v.y; d[2] = v.z; };
+        if (auto p = dynamic_cast<TriangleLight*>(li)) {
+            o.kind = IMBA_LIGHT_TRIANGLE; set3(o.intensity, p->emit_.intensity);
+            set3(o.p0, p->verts_[0]); set3(o.p1, p->verts_[1]); set3(o.p2, p->verts_[2]);
+        } else if (auto p = dynamic_cast<DirectionalLight*>(li)) {
+            o.kind = IMBA_LIGHT_DIRECTIONAL; set3(o.intensity, p->intensity_); set3(o.p0, p->dir_);
+        } else if (auto p = dynamic_cast<PointLight*>(li)) {
+            o.kind = IMBA_LIGHT_POINT; set3(o.intensity, p->intensity_); set3(o.p0, p->pos_);
+        } else if (auto p = dynamic_cast<SpotLight*>(li)) {
+            o.kind = IMBA_LIGHT_SPOT; set3(o.intensity, p->intensity_); set3(o.p0, p->pos_); set3(o.p1, p->normal_); o.angle = p->angle_;
+        } else if (dynamic_cast<EnvLight*>(li)) {
+            o.kind = IMBA_LIGHT_ENV;
+        } else return -3;
+        rs->lights.push_back(o);
+    }
+    d->mesh_count = (int)sc.mesh_count();
+    d->mesh_vertex_base = rs->mesh_vertex_base.data(); d->mesh_tri_base = rs->mesh_tri_base.data();
+    d->vertices = rs->vertices.data(); d->normals = rs->normals.data(); d->texcoords = rs->texcoords.data();
+    d->geom_normals = rs->geom_normals.data(); d->indices = rs->indices.data();
+    d->instance_count = (int)rs->instances.size(); d->instances = rs->instances.data();
+    d->material_count = (int)rs->materials.size(); d->materials = rs->materials.data();
+    d->light_count = (int)rs->lights.size(); d->lights = rs->lights.data();
+    d->texture_count = (int)rs->textures.size(); d->textures = rs->textures.data();
+    d->texels = rs->texels.data(); d->texel_count = (int64_t)rs->texels.size() / 4;
+    d->env_tex = -1; d->env_intensity = 0.0f; // TODO env maps (Car scene only; HDR missing)
+    d->bsphere_center[0] = sc.bounding_sphere().center.x; d->bsphere_center[1] = sc.bounding_sphere().center.y;
+    d->bsphere_center[2] = sc.bounding_sphere().center.z; d->bsphere_radius = sc.bounding_sphere().radius;
+    if (rs->gpu_layout) {
+        auto& td = sc.traversal_data_gpu();
+        d->accel_layout = IMBA_ACCEL_BVH2; d->root = td.root; d->nodes = td.nodes.data();
+        d->node_count = count_nodes<traversal_gpu::Node>(td.nodes.data(), td.root);
+        d->tris = (const imba_vec4*)td.tris.data(); d->tri_vec4_count = td.tris.size();
+        d->inst_nodes = (const imba_instance_node*)td.instances.data(); d->inst_node_count = (int)td.instances.size();
+        d->mask_count = (int)td.masks.size(); d->masks = (const imba_mask*)td.masks.data();
+        d->mask_buffer = (const uint8_t*)td.mask_buffer.data(); d->mask_buffer_size = td.mask_buffer.size();
+        d->mask_indices = td.indices.data(); d->mask_texcoords = (const imba_vec2*)td.texcoords.data(); d->mask_texcoord_count = td.texcoords.size();
+    } else {
+        auto& td = sc.traversal_data_cpu();
+        d->accel_layout = IMBA_ACCEL_MBVH4; d->root = td.root; d->nodes = td.nodes.data();
+        d->node_count = count_nodes<traversal_cpu::Node>(td.nodes.data(), td.root);
+        d->tris = (const imba_vec4*)td.tris.data(); d->tri_vec4_count = td.tris.size();
+        d->inst_nodes = (const imba_instance_node*)td.instances.data(); d->inst_node_count = (int)td.instances.size();
+        d->mask_count = (int)td.masks.size(); d->masks = (const imba_mask*)td.masks.data();
+        d->mask_buffer = (const uint8_t*)td.mask_buffer.data(); d->mask_buffer_size = td.mask_buffer.size();
+        d->mask_indices = td.indices.data(); d->mask_texcoords = (const imba_vec2*)td.texcoords.data(); d->mask_texcoord_count = td.texcoords.size();
+    }
+    return 0;
+}
+
+/// Full render with the reference's own scheduler and integrators (frontend/main.cpp:87-163 minus SDL).
+/// out_rgb: w*h*3 floats, the SUM over iterations (not normalised).  stats: [0] primary rays, [1] shadow rays.
+/// seconds: wall clock of the render() calls only (render_window.cpp:60-66).
+int ref_render(void* h, int algo, int w, int hgt, float fov, int spp, int iterations, int threads, int tile,
+               int max_path_len, int light_paths, int connections, int knn, float radius_factor,
+               float* out_rgb, uint64_t* stats, double* seconds, float* pixel_size_out) {
+    Quiet q;
+    auto rs = (RefScene*)h;
+    Scene& scene = *rs->scene;
+    UserSettings s;
+    s.width = w; s.height = hgt; s.fov = fov; s.concurrent_spp = spp; s.thread_count = threads; s.tile_size = tile;
+    s.max_path_len = max_path_len; s.light_path_count = light_paths > 0 ? light_paths : w * hgt / 2;
+    s.num_connections = connections; s.num_knn = knn; s.radius_factor = radius_factor;
+    s.traversal_platform = rs->gpu_layout ? UserSettings::gpu : UserSettings::cpu;
+    s.algorithm = (UserSettings::Algorithm)algo;
+    const bool gpu = rs->gpu_layout;
+
+    PerspectiveCamera cam(s.width, s.height, s.fov);
+    setup_camera(cam, rs->cam_pos, rs->cam_dir, rs->cam_up);
+    AtomicImage img(w, hgt); img.clear();
+    double secs = 0.0; uint64_t prim = 0, shad = 0; float px = 0.0f;
+    auto loop = [&](Integrator& integ) {
+        integ.preprocess(); px = integ.pixel_size();
+        auto t0 = std::chrono::high_resolution_clock::now();
+        for (int i = 0; i < iterations; ++i) integ.render(img);
+        secs = std::chrono::duration<double>(std::chrono::high_resolution_clock::now() - t0).count();
+    };
+    if (s.algorithm == UserSettings::PT) {
+        DefaultTileGen<PTState> ray_gen(s.width, s.height, s.concurrent_spp, s.tile_size);
+        TileScheduler<PTState, ShadowState> scheduler(ray_gen, scene, 1, s.thread_count, s.tile_size * s.tile_size * s.concurrent_spp, gpu);
+        PathTracer integ(scene, cam, scheduler, s.max_path_len);
+        loop(integ);
+        prim = scheduler.total_prim_rays_; shad = scheduler.total_shadow_rays_;
+    } else {
+        DefaultTileGen<VCMState> ray_gen(s.width, s.height, s.concurrent_spp, s.tile_size);
+        TileScheduler<VCMState, VCMShadowState> scheduler(ray_gen, scene, s.num_connections + 1, s.thread_count, s.tile_size * s.tile_size * s.concurrent_spp, gpu);
+        std::unique_ptr<Integrator> integ;
+        uint64_t lp = 0, ls = 0;
+        switch (s.algorithm) {
+            case UserSettings::BPT:    integ.reset(new BPT(scene, cam, scheduler, s)); break;
+            case UserSettings::PPM:    integ.reset(new PPM(scene, cam, scheduler, s)); break;
+            case UserSettings::LT:     integ.reset(new LT(scene, cam, scheduler, s)); break;
+            case UserSettings::VCM_PT: integ.reset(new VCM_PT(scene, cam, scheduler, s)); break;
+            default:                   integ.reset(new VCM(scene, cam, scheduler, s)); break;
+        }
+        loop(*integ);
+        switch (s.algorithm) {
+#define LS(T) { auto p = static_cast<T*>(integ.get()); lp = p->light_scheduler_.total_prim_rays_; ls = p->light_scheduler_.total_shadow_rays_; }
+            case UserSettings::BPT: LS(BPT) break; case UserSettings::PPM: LS(PPM) break; case UserSettings::LT: LS(LT) break;
+            case UserSettings::VCM_PT: LS(VCM_PT) break; default: LS(VCM) break;
+#undef LS
+        }
+        prim = scheduler.total_prim_rays_ + lp; shad = scheduler.total_shadow_rays_ + ls;
+        integ.reset();
+    }
+    for (int i = 0; i < w * hgt; ++i) { out_rgb[3 * i] = img.pixels()[i][0]; out_rgb[3 * i + 1] = img.pixels()[i][1]; out_rgb[3 * i + 2] = img.pixels()[i][2]; }
+    if (stats) { stats[0] = prim; stats[1] = shad; }
+    if (seconds) *seconds = secs;
+    if (pixel_size_out) *pixel_size_out = px;
+    return 0;
+}
+
+/// Camera rays exactly as PathTracer::render's sample function makes them (pt.cpp:168-177) for pixel
+/// centres + given jitter; rays[i] for pixel (x = i % w, y = i / w).
+int ref_camera_rays(void* h, int w, int hgt, float fov, const float* jitter_xy, imba_ray* rays) {
+    auto rs = (RefScene*)h;
+    PerspectiveCamera cam(w, hgt, fov);
+    setup_camera(cam, rs->cam_pos, rs->cam_dir, rs->cam_up);
+    for (int y = 0; y < hgt; ++y) for (int x = 0; x < w; ++x) {
+        const int i = y * w + x;
+        const float sx = (float)x + (jitter_xy ? jitter_xy[2 * i] : 0.5f), sy = (float)y + (jitter_xy ? jitter_xy[2 * i + 1] : 0.5f);
+        ::Ray r = cam.generate_ray(sx, sy);
+        memcpy(&rays[i], &r, sizeof(r));
+    }
+    return 0;
+}
+
+/// PathTracer::process_primary_rays (pt.cpp:82-160) on an injected batch.
+/// states: PTState[count] (40 B). Outputs: the compacted continuation queue and the shadow queue.
+/// fb_rgb (w*h*3, may be null) receives add_contribution()s.
+int ref_pt_shade_batch(void* h, int w, int hgt, float fov, int max_path_len, int count, const imba_ray* rays,
+                       const imba_hit* hits, const void* states, imba_ray* rays_out, void* states_out, int* out_count,
+                       imba_ray* shadow_rays, void* shadow_states, int* shadow_count, float* fb_rgb) {
+    Quiet q;
+    static_assert(sizeof(PTState) == 40 && sizeof(ShadowState) == 16, "state sizes");
+    auto rs = (RefScene*)h;
+    Scene& scene = *rs->scene;
+    PerspectiveCamera cam(w, hgt, fov);
+    setup_camera(cam, rs->cam_pos, rs->cam_dir, rs->cam_up);
+    BatchScheduler<PTState, ShadowState> sched(scene);
+    RayQueue<PTState> prim(count, false); RayQueue<ShadowState> shadow(count, false);
+    sched.prim = &prim; sched.shadow = &shadow;
+    const PTState* st = (const PTState*)states;
+    for (int i = 0; i < count; ++i) { ::Ray r; memcpy(&r, &rays[i], 32); prim.push(r, st[i]); }
+    memcpy(prim.hits(), hits, sizeof(Hit) * count);
+    PathTracer pt(scene, cam, sched, max_path_len);
+    AtomicImage img(w, hgt); img.clear();
+    pt.render(img);
+    *out_count = prim.size(); *shadow_count = shadow.size();
+    memcpy(rays_out, prim.rays(), 32 * prim.size()); memcpy(states_out, prim.states(), sizeof(PTState) * prim.size());
+    memcpy(shadow_rays, shadow.rays(), 32 * shadow.size()); memcpy(shadow_states, shadow.states(), sizeof(ShadowState) * shadow.size());
+    if (fb_rgb) for (int i = 0; i < w * hgt; ++i) { fb_rgb[3 * i] = img.pixels()[i][0]; fb_rgb[3 * i + 1] = img.pixels()[i][1]; fb_rgb[3 * i + 2] = img.pixels()[i][2]; }
+    return 0;
+}
+
+/// calculate_intersection (integrator.h:71-123) on a batch; out: 20 floats per hit
+/// (pos3, out_dir3, normal3, uv2, geom_normal3, u_tangent3, v_tangent3) + material index.
+int ref_calc_intersections(void* h, int count, const imba_ray* rays, const imba_hit* hits, float* out20, int* mat_out) {
+    auto rs = (RefScene*)h; Scene& scene = *rs->scene;
+    for (int i = 0; i < count; ++i) {
+        Hit hit; memcpy(&hit, &hits[i], 16); ::Ray r; memcpy(&r, &rays[i], 32);
+        if (hit.tri_id < 0) { mat_out[i] = -1; continue; }
+        Intersection is = calculate_intersection(scene, hit, r);
+        float* o = out20 + 20 * i;
+        o[0] = is.pos.x; o[1] = is.pos.y; o[2] = is.pos.z; o[3] = is.out_dir.x; o[4] = is.out_dir.y; o[5] = is.out_dir.z;
+        o[6] = is.normal.x; o[7] = is.normal.y; o[8] = is.normal.z; o[9] = is.uv.x; o[10] = is.uv.y;
+        o[11] = is.geom_normal.x; o[12] = is.geom_normal.y; o[13] = is.geom_normal.z;
+        o[14] = is.u_tangent.x; o[15] = is.u_tangent.y; o[16] = is.u_tangent.z; o[17] = is.v_tangent.x; o[18] = is.v_tangent.y; o[19] = is.v_tangent.z;
+        int m = -1; for (size_t k = 0; k < scene.material_count(); ++k) if (scene.material(k).get() == is.mat) { m = (int)k; break; }
+        mat_out[i] = m;
+    }
+    return 0;
+}
+
+/// RNG known-answer helper (render/random.h:15-47).
+void ref_rng_floats(uint64_t seed, int discard, int n, float* out, uint64_t* state_out) {
+    RNG rng(seed); rng.discard(discard);
+    for (int i = 0; i < n; ++i) out[i] = rng.random_float();
+    if (state_out) *state_out = rng.state_;
+}
+
+/// Seeding of primary-ray states (ray_gen.h:57-72) for a given seed_base: returns RNG state after discard.
+void ref_seed_states(uint64_t seed_base, int first, int count, int spp, uint64_t* states_out) {
+    for (int i = first; i < first + count; ++i) {
+        int pixel_idx = i / spp;
+        int seed = seed_base;
+        seed = 33 * seed ^ i; seed = 33 * seed ^ i; seed = 33 * seed ^ i; seed = 33 * seed ^ i;
+        RNG rng(seed);
+        rng.discard((seed % 5) + 16 + pixel_idx % 5);
+        states_out[i - first] = rng.state_;
+    }
+}
+
+int ref_struct_sizes(int* out) {
+    out[0] = sizeof(::Ray); out[1] = sizeof(Hit); out[2] = sizeof(RayState); out[3] = sizeof(ShadowState); out[4] = sizeof(PTState);
+    out[5] = sizeof(VCMState); out[6] = sizeof(VCMShadowState); out[7] = sizeof(Intersection); out[8] = sizeof(LightPathVertex);
+    out[9] = sizeof(VCMPhoton); out[10] = sizeof(traversal_cpu::Node); out[11] = sizeof(traversal_gpu::Node); out[12] = sizeof(InstanceNode);
+    return 13;
+}
+
+} // extern "C"

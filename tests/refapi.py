@@ -1,0 +1,165 @@
+"""TEST INFRASTRUCTURE: ctypes bindings of the oracle (oracle/liboracle.so) and of the reference host code compiled
+in place (oracle/_ref/libimba_ref.so).  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / reference
+arm may import this module; nothing in imbatracer_b200/ does."""
+import ctypes as C
+import os
+import shutil
+
+import numpy as np
+
+from imbatracer_b200 import abi
+from imbatracer_b200.scene import FlatScene, from_desc
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_SO = os.path.join(ROOT, "oracle", "liboracle.so")
+REF_SO = os.path.join(ROOT, "oracle", "_ref", "libimba_ref.so")
+REF_SCENES = os.path.join(ROOT, "oracle", "_ref", "scenes")  # scratch COPY of the reference's test/scenes (git-ignored)
+
+_oracle = None
+_ref = None
+
+ENTRY = {  # (layout, any_hit) -> symbol
+    (0, 0): "intersect_cpu_masked_instanced", (0, 1): "occluded_cpu_masked_instanced",
+    (1, 0): "intersect_gpu_masked_instanced", (1, 1): "occluded_gpu_masked_instanced",
+}
+
+
+def oracle():
+    global _oracle
+    if _oracle is None:
+        L = C.CDLL(ORACLE_SO)
+        vp, i32 = C.c_void_p, C.c_int32
+        for name in ENTRY.values():
+            getattr(L, name).argtypes = [i32] + [vp] * 9 + [i32]
+            getattr(L, name).restype = None
+            getattr(L, name + "_counted").argtypes = [i32] + [vp] * 9 + [i32, vp]
+            getattr(L, name + "_counted").restype = None
+        L.oracle_set_threads.argtypes = [i32]
+        L.oracle_get_threads.restype = i32
+        L.bvh8_walk.argtypes = [vp, vp, vp, C.c_uint32, vp, vp, i32, i32, vp]
+        _oracle = L
+    return _oracle
+
+
+def have_ref():
+    return os.path.exists(REF_SO)
+
+
+def ref():
+    global _ref
+    if _ref is None:
+        L = C.CDLL(REF_SO)
+        vp, i32, f32 = C.c_void_p, C.c_int32, C.c_float
+        L.ref_scene_load.restype = vp; L.ref_scene_load.argtypes = [C.c_char_p, i32]
+        L.ref_scene_free.restype = None; L.ref_scene_free.argtypes = [vp]
+        L.ref_scene_camera.argtypes = [vp, vp, vp, vp]
+        L.ref_scene_export.argtypes = [vp, C.POINTER(abi.SceneDesc)]
+        L.ref_render.argtypes = [vp, i32, i32, i32, f32] + [i32] * 8 + [f32, vp, vp, vp, vp]
+        L.ref_camera_rays.argtypes = [vp, i32, i32, f32, vp, vp]
+        L.ref_pt_shade_batch.argtypes = [vp, i32, i32, f32, i32, i32] + [vp] * 10
+        L.ref_calc_intersections.argtypes = [vp, i32, vp, vp, vp, vp]
+        L.ref_rng_floats.restype = None; L.ref_rng_floats.argtypes = [C.c_uint64, i32, i32, vp, vp]
+        L.ref_seed_states.restype = None; L.ref_seed_states.argtypes = [C.c_uint64, i32, i32, i32, vp]
+        L.ref_struct_sizes.argtypes = [vp]
+        _ref = L
+    return _ref
+
+
+def trace_oracle(scene: FlatScene, rays: np.ndarray, any_hit=False, counters=False, threads=0):
+    """Runs the CPU restatement on the reference-layout structure held by `scene`. Returns hits (and counters)."""
+    L = oracle()
+    L.oracle_set_threads(threads)
+    rays = np.ascontiguousarray(rays); assert rays.dtype == abi.RAY
+    hits = np.zeros(len(rays), abi.HIT)
+    a = scene.arrays
+    masks = a["masks"].ctypes.data if len(a["masks"]) else None
+    args = [scene.root, a["nodes"].ctypes.data, a["inst_nodes"].ctypes.data, a["tris"].ctypes.data, rays.ctypes.data,
+            hits.ctypes.data, a["mask_indices"].ctypes.data if masks else None, a["mask_texcoords"].ctypes.data if masks else None,
+            masks, a["mask_buffer"].ctypes.data if masks else None, len(rays)]
+    name = ENTRY[(scene.accel_layout, int(bool(any_hit)))]
+    if counters:
+        cnt = np.zeros((len(rays), 4), np.uint32)
+        getattr(L, name + "_counted")(*args, cnt.ctypes.data)
+        return hits, cnt
+    getattr(L, name)(*args)
+    return hits
+
+
+class Bvh8Host:
+    """Host arrays of the product's converted structure (imba_bvh8_build) -- for the CPU walker."""
+
+    def __init__(self, scene: FlatScene):
+        L = abi.lib()
+        a = scene.arrays
+        self.h = L.imba_bvh8_build(scene.accel_layout, scene.root, a["nodes"].ctypes.data, a["tris"].ctypes.data, a["inst_nodes"].ctypes.data)
+        if not self.h:
+            raise RuntimeError(abi.last_error())
+        p = [C.c_void_p() for _ in range(3)]; n = [C.c_int64() for _ in range(3)]; root = C.c_uint32(); depth = C.c_int32()
+        abi.check(L.imba_bvh8_arrays(self.h, p[0], n[0], p[1], n[1], p[2], n[2], root, depth))
+
+        def grab(ptr, count, dt):
+            buf = (C.c_uint8 * (count * dt.itemsize)).from_address(ptr.value)
+            return np.frombuffer(buf, dtype=dt, count=count).copy()
+
+        self.nodes = grab(p[0], n[0].value, abi.NODE8); self.tris = grab(p[1], n[1].value, abi.TRI48)
+        self.insts = grab(p[2], n[2].value, abi.INST64); self.top_root = root.value; self.max_depth = depth.value
+        L.imba_bvh8_free(self.h); self.h = None
+
+    def walk(self, rays, any_hit=False, stats=False):
+        rays = np.ascontiguousarray(rays); hits = np.zeros(len(rays), abi.HIT)
+        st = np.zeros((len(rays), 4), np.uint32) if stats else None
+        oracle().bvh8_walk(self.nodes.ctypes.data, self.tris.ctypes.data, self.insts.ctypes.data, self.top_root,
+                           rays.ctypes.data, hits.ctypes.data, len(rays), int(bool(any_hit)), st.ctypes.data if stats else None)
+        return (hits, st) if stats else hits
+
+
+def ensure_ref_scenes(reference_root="/root/reference"):
+    """Copies the reference's test scenes to a scratch dir (its loader writes .bvh caches next to them, scene.cpp:67)."""
+    if not os.path.isdir(REF_SCENES):
+        src = os.path.join(reference_root, "test", "scenes", "cornell")
+        if not os.path.isdir(src):
+            return None
+        os.makedirs(REF_SCENES, exist_ok=True)
+        shutil.copytree(src, os.path.join(REF_SCENES, "cornell"))
+    return REF_SCENES
+
+
+class RefScene:
+    """A scene loaded by the reference's own loader + SBVH builder + adapters."""
+
+    def __init__(self, scene_file, gpu_layout=False):
+        self.L = ref()
+        self.h = self.L.ref_scene_load(scene_file.encode(), int(gpu_layout))
+        if not self.h:
+            raise RuntimeError(f"reference loader failed on {scene_file}")
+        self.gpu_layout = gpu_layout
+
+    def close(self):
+        if self.h:
+            self.L.ref_scene_free(self.h); self.h = None
+
+    def flat(self, name="") -> FlatScene:
+        d = abi.SceneDesc()
+        rc = self.L.ref_scene_export(self.h, C.byref(d))
+        if rc != 0:
+            raise RuntimeError(f"ref_scene_export failed: {rc}")
+        s = from_desc(d, 1 if self.gpu_layout else 0)
+        cam = np.zeros(9, np.float32)
+        self.L.ref_scene_camera(self.h, cam[0:3].ctypes.data, cam[3:6].ctypes.data, cam[6:9].ctypes.data)
+        s.cam = cam; s.name = name
+        return s
+
+    def camera_rays(self, w, h, fov=60.0, jitter=None):
+        rays = np.zeros(w * h, abi.RAY)
+        j = None if jitter is None else np.ascontiguousarray(jitter, np.float32)
+        self.L.ref_camera_rays(self.h, w, h, fov, j.ctypes.data if j is not None else None, rays.ctypes.data)
+        return rays
+
+    def render(self, algo, w, h, fov=60.0, spp=1, iterations=1, threads=0, tile=256, max_path_len=10, light_paths=0,
+               connections=1, knn=10, radius_factor=2.0):
+        img = np.zeros((h, w, 3), np.float32); stats = np.zeros(2, np.uint64); secs = C.c_double(); px = C.c_float()
+        threads = threads or os.cpu_count()
+        rc = self.L.ref_render(self.h, algo, w, h, fov, spp, iterations, threads, tile, max_path_len, light_paths, connections, knn,
+                               radius_factor, img.ctypes.data, stats.ctypes.data, C.byref(secs), C.byref(px))
+        assert rc == 0
+        return img, {"primary_rays": int(stats[0]), "shadow_rays": int(stats[1]), "seconds": secs.value, "pixel_size": px.value}

@@ -1,0 +1,47 @@
+"""CPU tests of the drop-in boundary: the C-ABI library loads without a GPU, exports every symbol the header declares,
+and refuses to compute without a device (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from imbatracer_b200 import abi
+from tests.conftest import ROOT, load_scene
+
+
+def declared_functions():
+    src = open(os.path.join(ROOT, "include", "imba_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    names = re.findall(r"\b([a-z_0-9]+)\s*\(", src)
+    return sorted({n for n in names if n.startswith("imba_") or n.endswith("_masked_instanced")})
+
+
+def test_library_exports_every_declared_symbol():
+    L = C.CDLL(abi.LIB_PATH)
+    names = declared_functions()
+    assert len(names) >= 10
+    missing = [n for n in names if not hasattr(L, n)]
+    assert not missing, missing
+
+
+def test_no_cpu_fallback_without_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    flat = load_scene("cornell_org", "cpu")
+    d = flat.desc()
+    h = abi.lib().imba_scene_create(C.byref(d))
+    assert not h
+    assert "no CUDA device" in abi.last_error()
+
+
+def test_oracle_is_not_linked_into_the_product():
+    import subprocess
+    out = subprocess.run(["nm", "-D", "--defined-only", abi.LIB_PATH], stdout=subprocess.PIPE, text=True).stdout
+    assert "oracle" not in out and "bvh8_walk" not in out
+    for root, _, files in os.walk(os.path.join(ROOT, "imbatracer_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cpp", ".h")) :
+                text = open(os.path.join(root, f)).read()
+                assert "refapi" not in text and "liboracle" not in text, f

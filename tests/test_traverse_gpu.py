@@ -1,0 +1,187 @@
+"""GPU parity tests proper: the CUDA traversal (through the C ABI) against the CPU oracle on the same seeded ray
+batches, against the committed golden hits, and at full size through size-independent properties.
+Bar: bit-exact (tri_id, inst_id, t, u) for closest-hit; identical occluded/unoccluded flag for any-hit."""
+import hashlib
+
+import numpy as np
+import pytest
+
+from imbatracer_b200 import abi
+from tests.conftest import SCENE_NAMES, batch_for, load_hits, load_scene
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    assert torch.cuda.is_available()
+    torch.cuda.set_device(0)
+    return torch
+
+
+def device_trace(scene, rays, any_hit=False, counters=False):
+    import torch
+    from imbatracer_b200 import api
+    d_rays = api.rays_to_device(rays)
+    cnt = torch.zeros((len(rays), 4), dtype=torch.int32, device="cuda") if counters else None
+    hits = api.hits_from_device(scene.trace(d_rays, any_hit=any_hit, counters=cnt))
+    torch.cuda.synchronize()
+    return (hits, cnt.cpu().numpy().view(np.uint32)) if counters else hits
+
+
+@pytest.mark.parametrize("name", SCENE_NAMES)
+@pytest.mark.parametrize("layout", ["cpu", "gpu"])
+def test_closest_and_occluded_match_oracle_and_goldens(torch_cuda, name, layout):
+    from imbatracer_b200 import api
+    from tests import refapi
+    flat = load_scene(name, layout)
+    rays = batch_for(name, flat)
+    scene = api.Scene(flat)
+    try:
+        got = device_trace(scene, rays)
+        want = refapi.trace_oracle(flat, rays)
+        bad = np.nonzero(got.view(np.uint8).reshape(-1, 16) != want.view(np.uint8).reshape(-1, 16))[0]
+        assert got.tobytes() == want.tobytes(), (len(set(bad.tolist())), got[bad[:3]], want[bad[:3]])
+        g = load_hits(name)
+        assert hashlib.sha256(got.tobytes()).digest() == g[f"closest_{layout}_sha"].tobytes()
+        occ = device_trace(scene, rays, any_hit=True)
+        assert np.array_equal(np.packbits(occ["tri_id"] >= 0), g[f"occluded_{layout}"])
+        # instrumented variant gives the same hits and plausible counters
+        got2, cnt = device_trace(scene, rays, counters=True)
+        assert got2.tobytes() == want.tobytes()
+        assert cnt[:, 0].max() < 4096 and cnt[:, 3].max() + 6 <= 40
+        assert cnt[got["tri_id"] >= 0, 1].min() >= 1
+    finally:
+        scene.close()
+
+
+def test_host_buffer_path_and_ragged_sizes(torch_cuda):
+    """imba_trace_host = RayQueue::traverse_gpu (H2D, trace, D2H); sizes 0, 1, 63, 64, 65 and a multi-chunk batch."""
+    from imbatracer_b200 import api
+    from tests import refapi, raygen
+    flat = load_scene("cornell_water", "gpu")
+    scene = api.Scene(flat)
+    try:
+        base = raygen.random_rays(flat, 70000, 5)
+        for n in (0, 1, 63, 64, 65, 70000):
+            rays = base[:n].copy()
+            got = scene.trace_host(rays)
+            want = refapi.trace_oracle(flat, rays) if n else np.zeros(0, abi.HIT)
+            assert got.tobytes() == want.tobytes(), n
+        big = np.tile(base, 32)[: (1 << 21) + 12345]  # > 2 chunks of 2^20 rays
+        got = scene.trace_host(big)
+        want = refapi.trace_oracle(flat, base)
+        assert got[:70000].tobytes() == want.tobytes()
+        assert got[70000:140000].tobytes() == want.tobytes()
+        assert got[-12345:].tobytes() == np.tile(want, 32)[: (1 << 21) + 12345][-12345:].tobytes()
+    finally:
+        scene.close()
+
+
+def test_full_size_properties_4m_rays(torch_cuda):
+    """BASELINE.json configs[1] size (4 194 304 rays): properties that need no oracle pass over the whole batch --
+    (1) determinism across launches, (2) closest-hit and any-hit agree on hit/miss when tmin = 0 and tmax = inf,
+    (3) re-tracing with tmax = t_hit*(1-1e-6) misses or hits something nearer-or-equal, with tmax just above hits
+    the same triangle, (4) a permuted batch gives permuted hits; plus an oracle check on a 1/64 sample."""
+    import torch
+    from imbatracer_b200 import api
+    from tests import refapi, raygen
+    flat = load_scene("cornell_water", "gpu")
+    scene = api.Scene(flat)
+    try:
+        n = 1 << 22
+        rays = raygen.random_rays(flat, n, 77, tmax_mix=False)
+        rays["tmin"] = 0
+        d = api.rays_to_device(rays)
+        h1 = scene.trace(d).clone(); h2 = scene.trace(d).clone()
+        assert torch.equal(h1, h2)
+        occ = scene.trace(d, any_hit=True)
+        assert torch.equal(h1[:, 0] >= 0, occ[:, 0] >= 0)
+        perm = torch.randperm(n, device="cuda")
+        hp = scene.trace(d[perm].contiguous())
+        assert torch.equal(hp, h1[perm])
+        t = h1[:, 2].view(torch.float32)
+        hit = h1[:, 0] >= 0
+        d_above = d.clone(); d_above[:, 7] = torch.where(hit, t * (1 + 1e-5), d[:, 7])
+        ha = scene.trace(d_above)
+        assert torch.equal(ha[:, :2], h1[:, :2])
+        sample = slice(0, n, 64)
+        got = api.hits_from_device(h1[sample])
+        want = refapi.trace_oracle(flat, np.ascontiguousarray(rays[sample]))
+        assert got.tobytes() == want.tobytes()
+    finally:
+        scene.close()
+
+
+def test_masked_traversal_matches_oracle(torch_cuda):
+    """Alpha-masked geometry (core/mask.h, Sponza-style): synthetic checkerboard masks on two Cornell materials."""
+    from imbatracer_b200 import api
+    from tests import refapi
+    flat = load_scene("cornell_specular_front", "gpu")
+    a = flat.arrays
+    nmat = len(a["materials"])
+    rng = np.random.default_rng(3)
+    masks = np.zeros(nmat, abi.MASK); masks["width"] = 1; masks["height"] = 1; masks["offset"] = 0
+    buf = [np.ones(4, np.uint8)]
+    off = 4
+    for m in range(0, nmat, 2):
+        w, h = 8 + m, 5 + m
+        masks[m] = (w, h, off)
+        buf.append((rng.random(w * h) < 0.5).astype(np.uint8)); off += w * h
+    a["masks"] = masks; a["mask_buffer"] = np.concatenate(buf)
+    idx = a["indices"].reshape(-1, 4).copy()
+    a["mask_indices"] = np.ascontiguousarray(idx.reshape(-1))
+    tc = rng.random((len(a["vertices"]) // 4, 2)).astype(np.float32) * 3 - 1
+    a["mask_texcoords"] = np.ascontiguousarray(tc.reshape(-1))
+    rays = batch_for("cornell_specular_front", flat)
+    scene = api.Scene(flat)
+    try:
+        got = device_trace(scene, rays)
+        want = refapi.trace_oracle(flat, rays)
+        plain = refapi.trace_oracle(load_scene("cornell_specular_front", "gpu"), rays)
+        assert want.tobytes() != plain.tobytes()  # the masks do change results
+        assert got.tobytes() == want.tobytes()
+        occ = device_trace(scene, rays, any_hit=True)
+        assert np.array_equal(occ["tri_id"] >= 0, refapi.trace_oracle(flat, rays, any_hit=True)["tri_id"] >= 0)
+    finally:
+        scene.close()
+
+
+def test_l1_drop_in_entry_points(torch_cuda):
+    """The reference's own FFI symbols (core/traversal_interface.h:4-10): gpu variant on device arrays in the BVH2
+    layout, cpu variant on host arrays in the MBVH4 layout; count padded to 64 / 8 as RayQueue does (ray_queue.h:250,273)."""
+    import ctypes as C
+    import torch
+    from tests import refapi
+    L = abi.lib()
+    for layout, sym, align in (("gpu", "intersect_gpu_masked_instanced", 64), ("cpu", "intersect_cpu_masked_instanced", 8)):
+        flat = load_scene("cornell_instances", layout)
+        rays = batch_for("cornell_instances", flat)[:5003]
+        n = (len(rays) + align - 1) // align * align
+        padded = np.zeros(n, abi.RAY); padded[:len(rays)] = rays
+        want = refapi.trace_oracle(flat, padded)
+        want_occ = refapi.trace_oracle(flat, padded, any_hit=True)["tri_id"] >= 0
+        a = flat.arrays
+        fn = getattr(L, sym); fn_occ = getattr(L, sym.replace("intersect", "occluded"))
+        for f in (fn, fn_occ):
+            f.restype = None; f.argtypes = [C.c_int] + [C.c_void_p] * 9 + [C.c_int]
+        if layout == "gpu":
+            dev = {k: torch.from_numpy(a[k].view(np.uint8).reshape(-1).copy()).cuda() for k in ("nodes", "inst_nodes", "tris", "mask_indices", "mask_texcoords", "masks", "mask_buffer")}
+            d_rays = torch.from_numpy(padded.view(np.uint8).reshape(-1)).cuda()
+            d_hits = torch.zeros(n * 16, dtype=torch.uint8, device="cuda")
+            args = [flat.root, dev["nodes"].data_ptr(), dev["inst_nodes"].data_ptr(), dev["tris"].data_ptr(), d_rays.data_ptr(), d_hits.data_ptr(),
+                    dev["mask_indices"].data_ptr(), dev["mask_texcoords"].data_ptr(), dev["masks"].data_ptr(), dev["mask_buffer"].data_ptr(), n]
+            fn(*args)
+            got = d_hits.cpu().numpy().view(abi.HIT)
+            fn_occ(*args)
+            occ = d_hits.cpu().numpy().view(abi.HIT)["tri_id"] >= 0
+        else:
+            hits = np.zeros(n, abi.HIT)
+            args = [flat.root, a["nodes"].ctypes.data, a["inst_nodes"].ctypes.data, a["tris"].ctypes.data, padded.ctypes.data, hits.ctypes.data,
+                    a["mask_indices"].ctypes.data, a["mask_texcoords"].ctypes.data, a["masks"].ctypes.data, a["mask_buffer"].ctypes.data, n]
+            fn(*args); got = hits.copy()
+            fn_occ(*args); occ = hits["tri_id"] >= 0
+        assert got.tobytes() == want.tobytes(), layout
+        assert np.array_equal(occ, want_occ), layout
+    L.imba_l1_invalidate()
