@@ -58,6 +58,16 @@ class SceneDesc(C.Structure):
     ]
 
 
+class RenderSettings(C.Structure):
+    _fields_ = [("algorithm", C.c_int32), ("width", C.c_int32), ("height", C.c_int32), ("fov", C.c_float),
+                ("cam_pos", C.c_float * 3), ("cam_dir", C.c_float * 3), ("cam_up", C.c_float * 3),
+                ("spp", C.c_int32), ("max_path_len", C.c_int32), ("light_path_count", C.c_int32),
+                ("num_connections", C.c_int32), ("num_knn", C.c_int32), ("radius_factor", C.c_float),
+                ("seed", C.c_uint64), ("rank", C.c_int32), ("rank_count", C.c_int32)]
+
+
+ALGO = {"pt": 0, "bpt": 1, "vcm": 2, "ppm": 3, "vcm_pt": 4, "lt": 5}
+
 # numpy dtypes of the ABI records
 RAY = np.dtype([("org", "<f4", 3), ("tmin", "<f4"), ("dir", "<f4", 3), ("tmax", "<f4")])
 HIT = np.dtype([("tri_id", "<i4"), ("inst_id", "<i4"), ("tmax", "<f4"), ("u", "<f4")])
@@ -75,6 +85,10 @@ TEXTURE = np.dtype([("width", "<i4"), ("height", "<i4"), ("offset", "<i8")])
 MASK = np.dtype([("width", "<i4"), ("height", "<i4"), ("offset", "<i4")])
 NODE8 = np.dtype([("p", "<f4", 3), ("e", "u1", 3), ("imask", "u1"), ("child_base", "<u4"), ("prim_base", "<u4"),
                   ("meta", "u1", 8), ("q", "u1", (6, 8))])
+PT_STATE = np.dtype([("pixel_id", "<i4"), ("sample_id", "<i4"), ("rng", "<u8"), ("throughput", "<f4", 3), ("bounces_spec", "<u4"),
+                     ("last_pdf", "<f4"), ("pad", "<u4")])
+SHADOW_STATE = np.dtype([("pixel_id", "<i4"), ("throughput", "<f4", 3)])
+assert PT_STATE.itemsize == 40 and SHADOW_STATE.itemsize == 16
 TRI48 = np.dtype([("v0", "<f4", 3), ("id", "<i4"), ("e1", "<f4", 3), ("pad0", "<f4"), ("e2", "<f4", 3), ("pad1", "<f4")])
 INST64 = np.dtype([("m", "<f4", 12), ("inst_id", "<i4"), ("root", "<i4"), ("pad", "<i4", 2)])
 assert RAY.itemsize == 32 and HIT.itemsize == 16 and NODE4.itemsize == 112 and NODE2.itemsize == 56
@@ -108,6 +122,26 @@ def lib():
     L.imba_bvh8_free.restype = None; L.imba_bvh8_free.argtypes = [vp]
     L.imba_bvh8_arrays.argtypes = [vp, C.POINTER(vp), C.POINTER(i64), C.POINTER(vp), C.POINTER(i64), C.POINTER(vp),
                                    C.POINTER(i64), C.POINTER(C.c_uint32), C.POINTER(i32)]
+    f32, u32 = C.c_float, C.c_uint32
+    L.imba_integrator_create.restype = vp; L.imba_integrator_create.argtypes = [vp, C.POINTER(RenderSettings)]
+    L.imba_integrator_destroy.restype = None; L.imba_integrator_destroy.argtypes = [vp]
+    L.imba_integrator_preprocess.argtypes = [vp]
+    L.imba_integrator_pixel_size.restype = f32; L.imba_integrator_pixel_size.argtypes = [vp]
+    L.imba_integrator_reset.argtypes = [vp]
+    L.imba_integrator_render.argtypes = [vp, i32]
+    L.imba_integrator_framebuffer.restype = vp; L.imba_integrator_framebuffer.argtypes = [vp]
+    L.imba_integrator_set_framebuffer.argtypes = [vp, vp]
+    L.imba_integrator_stream.restype = vp; L.imba_integrator_stream.argtypes = [vp]
+    L.imba_integrator_sync.argtypes = [vp]
+    L.imba_integrator_download.argtypes = [vp, vp]
+    L.imba_integrator_clear.argtypes = [vp]
+    L.imba_integrator_ray_counts.argtypes = [vp, vp]
+    L.imba_integrator_camera_rays.argtypes = [vp, i32, vp, vp]
+    L.imba_seed_states.argtypes = [u32, i32, i32, i32, vp]
+    L.imba_pt_shade_batch.argtypes = [vp, i32] + [vp] * 9
+    L.imba_queue_sort_by_material.argtypes = [vp, vp, i32, vp, vp, vp]
+    L.imba_queue_compact_rays.argtypes = [vp, vp, i32, vp, vp, i32, vp, vp]
+    L.imba_queue_compact_hits.argtypes = [vp, vp, vp, vp, i32, vp, vp, vp, i32, vp, vp]
     _lib = L
     return L
 

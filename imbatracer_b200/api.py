@@ -66,3 +66,83 @@ def rays_to_device(rays: np.ndarray, device="cuda"):
 
 def hits_from_device(hits) -> np.ndarray:
     return hits.cpu().numpy().reshape(-1, 4).copy().view(abi.HIT).reshape(-1)
+
+
+def render_settings(flat, algorithm="pt", width=512, height=512, fov=60.0, spp=1, max_path_len=10, light_path_count=0,
+                    num_connections=1, num_knn=10, radius_factor=2.0, seed=1, rank=0, rank_count=1):
+    """UserSettings defaults of the reference (frontend/cmd_line.h:61-79) + the camera of the .scene file."""
+    s = abi.RenderSettings()
+    s.algorithm = abi.ALGO[algorithm]; s.width = width; s.height = height; s.fov = fov
+    s.cam_pos[:] = [float(x) for x in flat.cam[0:3]]; s.cam_dir[:] = [float(x) for x in flat.cam[3:6]]; s.cam_up[:] = [float(x) for x in flat.cam[6:9]]
+    s.spp = spp; s.max_path_len = max_path_len; s.light_path_count = light_path_count or width * height // 2
+    s.num_connections = num_connections; s.num_knn = num_knn; s.radius_factor = radius_factor
+    s.seed = seed; s.rank = rank; s.rank_count = rank_count
+    return s
+
+
+class Integrator:
+    """imba_integrator: Integrator::{preprocess, render, reset, pixel_size} on the device (integrator.h:19-39)."""
+
+    def __init__(self, scene: Scene, settings: abi.RenderSettings):
+        self.L = abi.lib(); self.scene = scene; self.settings = settings
+        self.h = self.L.imba_integrator_create(scene.h, C.byref(settings))
+        if not self.h:
+            raise RuntimeError("imba_integrator_create failed: " + abi.last_error())
+
+    def close(self):
+        if self.h:
+            self.L.imba_integrator_destroy(self.h); self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def preprocess(self):
+        abi.check(self.L.imba_integrator_preprocess(self.h), "imba_integrator_preprocess")
+        return self.L.imba_integrator_pixel_size(self.h)
+
+    def render(self, iterations=1):
+        abi.check(self.L.imba_integrator_render(self.h, iterations), "imba_integrator_render")
+
+    def sync(self):
+        abi.check(self.L.imba_integrator_sync(self.h), "imba_integrator_sync")
+
+    def clear(self):
+        abi.check(self.L.imba_integrator_clear(self.h), "imba_integrator_clear")
+
+    def set_framebuffer(self, tensor):
+        assert tensor.is_cuda and tensor.dtype.is_floating_point and tensor.numel() == self.settings.width * self.settings.height * 3
+        self._fb = tensor
+        abi.check(self.L.imba_integrator_set_framebuffer(self.h, tensor.data_ptr()), "imba_integrator_set_framebuffer")
+
+    def stream_ptr(self):
+        return self.L.imba_integrator_stream(self.h)
+
+    def download(self):
+        img = np.empty((self.settings.height, self.settings.width, 3), np.float32)
+        abi.check(self.L.imba_integrator_download(self.h, img.ctypes.data), "imba_integrator_download")
+        return img
+
+    def ray_counts(self):
+        out = np.zeros(2, np.uint64)
+        abi.check(self.L.imba_integrator_ray_counts(self.h, out.ctypes.data), "imba_integrator_ray_counts")
+        return int(out[0]), int(out[1])
+
+    def camera_rays(self, raster_xy):
+        xy = np.ascontiguousarray(raster_xy, np.float32).reshape(-1, 2)
+        rays = np.zeros(len(xy), abi.RAY)
+        abi.check(self.L.imba_integrator_camera_rays(self.h, len(xy), xy.ctypes.data, rays.ctypes.data), "camera_rays")
+        return rays
+
+    def pt_shade_batch(self, rays, hits, states):
+        n = len(rays)
+        assert rays.dtype == abi.RAY and hits.dtype == abi.HIT and states.dtype == abi.PT_STATE
+        rays_out = np.zeros(n, abi.RAY); states_out = np.zeros(n, abi.PT_STATE)
+        sh_rays = np.zeros(n, abi.RAY); sh_states = np.zeros(n, abi.SHADOW_STATE)
+        nc, ns = C.c_int(), C.c_int()
+        abi.check(self.L.imba_pt_shade_batch(self.h, n, rays.ctypes.data, hits.ctypes.data, states.ctypes.data, rays_out.ctypes.data,
+                                             states_out.ctypes.data, C.addressof(nc), sh_rays.ctypes.data, sh_states.ctypes.data, C.addressof(ns)),
+                  "imba_pt_shade_batch")
+        return rays_out[:nc.value], states_out[:nc.value], sh_rays[:ns.value], sh_states[:ns.value]

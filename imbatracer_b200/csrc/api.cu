@@ -97,29 +97,36 @@ extern "C" int imba_scene_stats(const imba_scene* s, int64_t out[5]) {
     return IMBA_OK;
 }
 
-int imba_scene_trace(imba_scene* s, const imba_ray* d_rays, imba_hit* d_hits, int count, int any_hit, uint32_t* d_counters,
-                     cudaStream_t stream) {
-    if (!s || count < 0 || (count > 0 && (!d_rays || !d_hits))) { imba_set_error("invalid traversal arguments"); return IMBA_ERR_INVALID; }
-    if (count == 0) return IMBA_OK;
-    const bool any = any_hit != 0, masks = s->has_masks, stats = d_counters != nullptr;
-    const int variant = (any ? 4 : 0) | (masks ? 2 : 0) | (stats ? 1 : 0);
+int imba_scene_trace_ex(imba_scene* s, const TraceRequest& rq, cudaStream_t stream) {
+    if (!s || rq.capacity < 0 || (rq.capacity > 0 && !rq.d_rays)) { imba_set_error("invalid traversal arguments"); return IMBA_ERR_INVALID; }
+    if (rq.capacity == 0) return IMBA_OK;
+    const bool masks = s->has_masks, stats = rq.d_counters != nullptr;
+    const int variant = rq.mode * 4 + (masks ? 2 : 0) + (stats ? 1 : 0);
     if (s->grid_cache[variant] == 0) {
-        const int per_sm = imba_trace_blocks_per_sm(any, masks, stats);
+        const int per_sm = imba_trace_blocks_per_sm(rq.mode, masks, stats);
         if (per_sm <= 0) { imba_set_error("traversal kernel cannot be resident (occupancy 0): %s", cudaGetErrorString(cudaGetLastError())); return IMBA_ERR_CUDA; }
         s->grid_cache[variant] = per_sm * s->sm_count;
     }
     const int warps_per_block = imba_trace_block_threads() / 32;
-    const int needed = (count + 32 * warps_per_block - 1) / (32 * warps_per_block);
+    const int needed = (rq.capacity + 32 * warps_per_block - 1) / (32 * warps_per_block);
     const int grid = needed < s->grid_cache[variant] ? needed : s->grid_cache[variant];
     unsigned* ctr = s->d_counters + (s->next_counter.fetch_add(1) % imba_scene::kCounters);
     IMBA_CUDA(cudaMemsetAsync(ctr, 0, sizeof(unsigned), stream), IMBA_ERR_CUDA);
     TraceArgs a;
     a.nodes = s->d_nodes; a.tris = s->d_tris; a.insts = s->d_insts; a.top_root = s->top_root;
-    a.rays = (const float4*)d_rays; a.hits = (int4*)d_hits; a.count = count; a.counter = ctr; a.stats = d_counters;
+    a.rays = (const float4*)rq.d_rays; a.hits = (int4*)rq.d_hits; a.count = rq.capacity; a.count_ptr = rq.d_count; a.counter = ctr; a.stats = rq.d_counters;
     a.indices = s->d_mask_indices; a.texcoords = s->d_mask_texcoords; a.masks = s->d_masks; a.mask_buffer = s->d_mask_buffer;
-    IMBA_CUDA(imba_launch_trace(a, any, masks, stats, grid, stream), IMBA_ERR_CUDA);
+    a.shadow_states = rq.d_shadow_states; a.framebuffer = rq.d_framebuffer;
+    IMBA_CUDA(imba_launch_trace(a, rq.mode, masks, stats, grid, stream), IMBA_ERR_CUDA);
     g_imba_launches.fetch_add(1);
     return IMBA_OK;
+}
+
+int imba_scene_trace(imba_scene* s, const imba_ray* d_rays, imba_hit* d_hits, int count, int any_hit, uint32_t* d_counters,
+                     cudaStream_t stream) {
+    if (count > 0 && !d_hits) { imba_set_error("invalid traversal arguments"); return IMBA_ERR_INVALID; }
+    TraceRequest rq; rq.d_rays = d_rays; rq.d_hits = d_hits; rq.capacity = count; rq.mode = any_hit ? 1 : 0; rq.d_counters = d_counters;
+    return imba_scene_trace_ex(s, rq, stream);
 }
 
 extern "C" int imba_trace(imba_scene* s, const imba_ray* d_rays, imba_hit* d_hits, int count, int any_hit,

@@ -40,12 +40,21 @@ struct imba_scene {
     cudaStream_t stage_stream[2] = { nullptr, nullptr };
     // shading data (geometry, materials, lights, textures), null until uploaded
     DeviceShading* shading = nullptr;
-    int grid_cache[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
+    int grid_cache[12] = { 0 };
 };
 
 /* Uploads a converted structure; fills scene->d_nodes etc. */
 int imba_scene_upload_accel(imba_scene* s, const Bvh8& b);
 /* Launches traversal on device buffers. */
+struct TraceRequest {
+    const imba_ray* d_rays = nullptr; imba_hit* d_hits = nullptr;
+    int capacity = 0;               // upper bound of the ray count (sizes the grid)
+    const int* d_count = nullptr;   // optional device-resident ray count
+    int mode = 0;                   // 0 closest, 1 any hit, 2 any hit + shadow resolve
+    uint32_t* d_counters = nullptr;
+    const void* d_shadow_states = nullptr; float* d_framebuffer = nullptr;
+};
+int imba_scene_trace_ex(imba_scene* s, const TraceRequest& rq, cudaStream_t stream);
 int imba_scene_trace(imba_scene* s, const imba_ray* d_rays, imba_hit* d_hits, int count, int any_hit, uint32_t* d_counters,
                      cudaStream_t stream);
 

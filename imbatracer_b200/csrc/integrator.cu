@@ -1,0 +1,308 @@
+/* integrator.cu -- host side of the device-resident integrators behind Integrator::{render,reset,preprocess,
+ * pixel_size} (render/integrators/integrator.h:19-39) and RayScheduler::run_iteration (ray_scheduler.h:29-32).
+ *
+ * The reference runs one primary + one shadow queue per CPU thread over 256x256 tiles (tile_scheduler.h:100-144).  Here
+ * one iteration is ONE wavefront over all width*height*spp samples, every stage a kernel on one stream, queue sizes in
+ * device memory: nothing synchronises with the host until the caller downloads the framebuffer.
+ *   per wavefront:  closest-hit trace -> sort hits by material -> shade (emit / NEE / bounce) ->
+ *                   any-hit trace fused with the shadow resolve -> stable compaction into the ping-pong queue
+ */
+#include "integrator.cuh"
+#include <cstring>
+
+struct imba_integrator {
+    imba_scene* scene = nullptr;
+    imba_render_settings cfg;
+    DevCamera cam;
+    cudaStream_t stream = nullptr;
+    int capacity = 0;
+    int state_bytes = sizeof(PTState);
+    float4* rays[2] = { nullptr, nullptr };
+    char*   states[2] = { nullptr, nullptr };
+    int*    count[2] = { nullptr, nullptr };
+    int4*   hits = nullptr;
+    float4* shadow_rays = nullptr; ShadowState* shadow_states = nullptr;
+    PartitionBuffers part;
+    float*  fb = nullptr; bool owns_fb = true;
+    unsigned long long* d_stats = nullptr;   // [0] primary rays, [1] shadow rays
+    float*  d_probe = nullptr;               // [0] total (float), [1] count (int)
+    uint64_t iteration = 0;
+    float   pixel_size = 1.0f;
+};
+
+static DevCamera make_camera(const imba_render_settings& s) {
+    // CameraControl::setup (frontend/main.cpp:64-71) followed by PerspectiveCamera::move (camera.h:27-50), in double
+    auto norm = [](double* v) { const double l = sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]); v[0] /= l; v[1] /= l; v[2] /= l; };
+    auto cross3 = [](const double* a, const double* b, double* o) { o[0] = a[1] * b[2] - a[2] * b[1]; o[1] = a[2] * b[0] - a[0] * b[2]; o[2] = a[0] * b[1] - a[1] * b[0]; };
+    double dir[3] = { s.cam_dir[0], s.cam_dir[1], s.cam_dir[2] }, up[3] = { s.cam_up[0], s.cam_up[1], s.cam_up[2] }, right[3], down[3];
+    norm(dir); norm(up);
+    cross3(dir, up, right); norm(right);
+    cross3(right, dir, up); norm(up);       // orthogonalised up (main.cpp:69)
+    cross3(dir, up, right); norm(right);    // camera.h:29
+    cross3(dir, right, down);               // camera.h:30: "up" of the camera matrix points down the image
+    DevCamera c;
+    c.px = s.cam_pos[0]; c.py = s.cam_pos[1]; c.pz = s.cam_pos[2];
+    c.dx = (float)dir[0]; c.dy = (float)dir[1]; c.dz = (float)dir[2];
+    c.rx = (float)right[0]; c.ry = (float)right[1]; c.rz = (float)right[2];
+    c.ux = (float)down[0]; c.uy = (float)down[1]; c.uz = (float)down[2];
+    c.tan_half = (float)tan((double)s.fov * 3.14159265358979323846 / 360.0);
+    c.width = s.width; c.height = s.height;
+    c.img_plane_dist = (float)s.width / (2.0f * c.tan_half);
+    return c;
+}
+
+static uint32_t iteration_seed(uint64_t seed, uint64_t global_iteration, uint32_t stream_id) {
+    // splitmix64 of (seed, iteration, stream): replaces std::random_device (ray_gen.h:49-50) so runs are reproducible
+    uint64_t z = seed + 0x9E3779B97F4A7C15ull * (global_iteration * 4 + stream_id + 1);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull; z = (z ^ (z >> 27)) * 0x94D049BB133111EBull; z ^= z >> 31;
+    return (uint32_t)z;
+}
+
+extern "C" void imba_integrator_destroy(imba_integrator* it) {
+    if (!it) return;
+    for (int i = 0; i < 2; ++i) { cudaFree(it->rays[i]); cudaFree(it->states[i]); cudaFree(it->count[i]); }
+    cudaFree(it->hits); cudaFree(it->shadow_rays); cudaFree(it->shadow_states);
+    imba_partition_free(it->part);
+    if (it->owns_fb) cudaFree(it->fb);
+    cudaFree(it->d_stats); cudaFree(it->d_probe);
+    if (it->stream) cudaStreamDestroy(it->stream);
+    delete it;
+}
+
+extern "C" imba_integrator* imba_integrator_create(imba_scene* scene, const imba_render_settings* s) {
+    if (!scene || !s || !imba_shading_view(scene)) { imba_set_error("integrator needs a scene created with geometry, materials and lights"); return nullptr; }
+    if (s->width <= 0 || s->height <= 0 || s->spp <= 0 || s->max_path_len <= 0) { imba_set_error("invalid render settings"); return nullptr; }
+    if (s->algorithm != IMBA_ALGO_PT) { imba_set_error("algorithm %d is not available on the device yet (PT only)", s->algorithm); return nullptr; }
+    if (imba_shading_view(scene)->light_count <= 0) { imba_set_error("scene has no lights"); return nullptr; }
+    if (imba_shading_view(scene)->material_count > 1023) { imba_set_error("more than 1023 materials"); return nullptr; }
+    imba_integrator* it = new imba_integrator;
+    it->scene = scene; it->cfg = *s; it->cam = make_camera(*s);
+    if (it->cfg.rank_count <= 0) { it->cfg.rank_count = 1; it->cfg.rank = 0; }
+    const long long cap = (long long)s->width * s->height * s->spp;
+    if (cap > (1ll << 30)) { imba_set_error("queue capacity too large"); delete it; return nullptr; }
+    it->capacity = (int)cap;
+    bool ok = cudaStreamCreateWithFlags(&it->stream, cudaStreamNonBlocking) == cudaSuccess;
+    for (int i = 0; i < 2 && ok; ++i) {
+        ok = ok && cudaMalloc((void**)&it->rays[i], (size_t)cap * 32) == cudaSuccess;
+        ok = ok && cudaMalloc((void**)&it->states[i], (size_t)cap * it->state_bytes) == cudaSuccess;
+        ok = ok && cudaMalloc((void**)&it->count[i], 16) == cudaSuccess;
+    }
+    ok = ok && cudaMalloc((void**)&it->hits, (size_t)cap * 16) == cudaSuccess;
+    ok = ok && cudaMalloc((void**)&it->shadow_rays, (size_t)cap * 32) == cudaSuccess;
+    ok = ok && cudaMalloc((void**)&it->shadow_states, (size_t)cap * 16) == cudaSuccess;
+    ok = ok && imba_partition_alloc(it->part, it->capacity, imba_shading_view(scene)->material_count + 1) == cudaSuccess;
+    ok = ok && cudaMalloc((void**)&it->fb, (size_t)s->width * s->height * 3 * sizeof(float)) == cudaSuccess;
+    ok = ok && cudaMalloc((void**)&it->d_stats, 16) == cudaSuccess && cudaMalloc((void**)&it->d_probe, 16) == cudaSuccess;
+    ok = ok && cudaMemset(it->fb, 0, (size_t)s->width * s->height * 3 * sizeof(float)) == cudaSuccess && cudaMemset(it->d_stats, 0, 16) == cudaSuccess;
+    if (!ok) { imba_set_error("integrator allocation failed: %s", cudaGetErrorString(cudaGetLastError())); imba_integrator_destroy(it); return nullptr; }
+    return it;
+}
+
+extern "C" int imba_integrator_set_framebuffer(imba_integrator* it, float* d_rgb) {
+    if (!it || !d_rgb) { imba_set_error("null argument"); return IMBA_ERR_INVALID; }
+    if (it->owns_fb) cudaFree(it->fb);
+    it->fb = d_rgb; it->owns_fb = false;
+    return IMBA_OK;
+}
+
+extern "C" void* imba_integrator_stream(imba_integrator* it) { return it ? (void*)it->stream : nullptr; }
+
+extern "C" int imba_integrator_preprocess(imba_integrator* it) {
+    if (!it) { imba_set_error("null argument"); return IMBA_ERR_INVALID; }
+    const int quads = ((it->cam.width + 7) / 8) * ((it->cam.height + 7) / 8);
+    const int n = std::min(quads * 4, it->capacity / 4 * 4);
+    IMBA_CUDA(cudaMemsetAsync(it->d_probe, 0, 16, it->stream), IMBA_ERR_CUDA);
+    IMBA_CUDA(imba_probe_raygen(it->cam, it->rays[0], n, it->stream), IMBA_ERR_CUDA);
+    int rc = imba_scene_trace(it->scene, (const imba_ray*)it->rays[0], (imba_hit*)it->hits, n, 0, nullptr, it->stream);
+    if (rc != IMBA_OK) return rc;
+    IMBA_CUDA(imba_probe_reduce(it->rays[0], it->hits, n / 4, it->d_probe, (int*)(it->d_probe + 1), it->stream), IMBA_ERR_CUDA);
+    g_imba_launches.fetch_add(2);
+    float h[2]; IMBA_CUDA(cudaMemcpyAsync(h, it->d_probe, 8, cudaMemcpyDeviceToHost, it->stream), IMBA_ERR_CUDA);
+    IMBA_CUDA(cudaStreamSynchronize(it->stream), IMBA_ERR_CUDA);
+    int cnt; memcpy(&cnt, &h[1], 4);
+    it->pixel_size = cnt == 0 ? 1.0f : h[0] / (float)cnt;
+    return IMBA_OK;
+}
+
+extern "C" float imba_integrator_pixel_size(const imba_integrator* it) { return it ? it->pixel_size : 0.0f; }
+extern "C" int imba_integrator_reset(imba_integrator* it) { if (!it) return IMBA_ERR_INVALID; it->iteration = 0; return IMBA_OK; }
+
+static int pt_wavefront(imba_integrator* it, int cur, int capacity) {
+    const DeviceShading& S = *imba_shading_view(it->scene);
+    TraceRequest rq; rq.d_rays = (const imba_ray*)it->rays[cur]; rq.d_hits = (imba_hit*)it->hits; rq.capacity = capacity; rq.d_count = it->count[cur]; rq.mode = 0;
+    int rc = imba_scene_trace_ex(it->scene, rq, it->stream);
+    if (rc != IMBA_OK) return rc;
+    IMBA_CUDA(imba_sort_hits_by_material(it->part, it->hits, S.indices, S.material_count, (int*)it->shadow_states, it->count[cur], 0, capacity, it->stream), IMBA_ERR_CUDA);
+    IMBA_CUDA(imba_pt_shade(S, it->rays[cur], it->hits, (PTState*)it->states[cur], it->part.indices, it->part.bin_start + S.material_count, it->count[cur], capacity,
+                            it->shadow_rays, it->shadow_states, it->fb, it->cfg.max_path_len, it->d_stats, it->stream), IMBA_ERR_CUDA);
+    TraceRequest sq; sq.d_rays = (const imba_ray*)it->shadow_rays; sq.capacity = capacity; sq.d_count = it->count[cur]; sq.mode = 2;
+    sq.d_shadow_states = it->shadow_states; sq.d_framebuffer = it->fb;
+    rc = imba_scene_trace_ex(it->scene, sq, it->stream);
+    if (rc != IMBA_OK) return rc;
+    IMBA_CUDA(imba_compact_alive(it->part, it->hits, it->rays[cur], it->states[cur], it->state_bytes, it->count[cur], 0, capacity,
+                                 it->rays[cur ^ 1], it->states[cur ^ 1], it->count[cur ^ 1], it->stream), IMBA_ERR_CUDA);
+    g_imba_launches.fetch_add(3 + 1 + 4);
+    return IMBA_OK;
+}
+
+extern "C" int imba_integrator_render(imba_integrator* it, int iterations) {
+    if (!it || iterations < 0) { imba_set_error("invalid argument"); return IMBA_ERR_INVALID; }
+    for (int k = 0; k < iterations; ++k, ++it->iteration) {
+        const uint64_t global_iter = it->iteration * (uint64_t)it->cfg.rank_count + (uint64_t)it->cfg.rank;
+        const uint32_t seed_base = iteration_seed(it->cfg.seed, global_iter, 0);
+        IMBA_CUDA(imba_pt_raygen(it->cam, it->cfg.spp, seed_base, 0, it->capacity, it->rays[0], (PTState*)it->states[0], it->count[0], it->stream), IMBA_ERR_CUDA);
+        g_imba_launches.fetch_add(1);
+        int cur = 0;
+        for (int wave = 0; wave < it->cfg.max_path_len; ++wave, cur ^= 1) {
+            const int rc = pt_wavefront(it, cur, it->capacity);
+            if (rc != IMBA_OK) return rc;
+        }
+    }
+    return IMBA_OK;
+}
+
+extern "C" float* imba_integrator_framebuffer(imba_integrator* it) { return it ? it->fb : nullptr; }
+
+extern "C" int imba_integrator_sync(imba_integrator* it) {
+    if (!it) return IMBA_ERR_INVALID;
+    IMBA_CUDA(cudaStreamSynchronize(it->stream), IMBA_ERR_CUDA);
+    return IMBA_OK;
+}
+
+extern "C" int imba_integrator_download(imba_integrator* it, float* h_rgb) {
+    if (!it || !h_rgb) { imba_set_error("null argument"); return IMBA_ERR_INVALID; }
+    IMBA_CUDA(cudaMemcpyAsync(h_rgb, it->fb, (size_t)it->cfg.width * it->cfg.height * 3 * sizeof(float), cudaMemcpyDeviceToHost, it->stream), IMBA_ERR_CUDA);
+    IMBA_CUDA(cudaStreamSynchronize(it->stream), IMBA_ERR_CUDA);
+    return IMBA_OK;
+}
+
+extern "C" int imba_integrator_clear(imba_integrator* it) {
+    if (!it) return IMBA_ERR_INVALID;
+    IMBA_CUDA(cudaMemsetAsync(it->fb, 0, (size_t)it->cfg.width * it->cfg.height * 3 * sizeof(float), it->stream), IMBA_ERR_CUDA);
+    IMBA_CUDA(cudaMemsetAsync(it->d_stats, 0, 16, it->stream), IMBA_ERR_CUDA);
+    return IMBA_OK;
+}
+
+extern "C" int imba_integrator_ray_counts(imba_integrator* it, uint64_t out[2]) {
+    if (!it || !out) return IMBA_ERR_INVALID;
+    unsigned long long h[2];
+    IMBA_CUDA(cudaMemcpyAsync(h, it->d_stats, 16, cudaMemcpyDeviceToHost, it->stream), IMBA_ERR_CUDA);
+    IMBA_CUDA(cudaStreamSynchronize(it->stream), IMBA_ERR_CUDA);
+    out[0] = h[0]; out[1] = h[1];
+    return IMBA_OK;
+}
+
+/* Camera rays of the integrator's camera for given raster positions (parity harness for camera.h:57-65). */
+extern "C" int imba_integrator_camera_rays(imba_integrator* it, int count, const float* raster_xy, imba_ray* h_rays) {
+    if (!it || !raster_xy || !h_rays) return IMBA_ERR_INVALID;
+    for (int i = 0; i < count; ++i) {
+        const V3 d = it->cam.ray_dir(raster_xy[2 * i], raster_xy[2 * i + 1]);
+        h_rays[i].org = imba_vec4{ it->cam.px, it->cam.py, it->cam.pz, 0.0f };
+        h_rays[i].dir = imba_vec4{ d.x, d.y, d.z, FLT_MAX };
+    }
+    return IMBA_OK;
+}
+
+/* RNG states of primary rays first .. first+count-1 for a given seed_base (parity harness for ray_gen.h:57-72). */
+extern "C" int imba_seed_states(uint32_t seed_base, int first, int count, int spp, uint64_t* out) {
+    if (!out || spp <= 0) return IMBA_ERR_INVALID;
+    for (int i = first; i < first + count; ++i) out[i - first] = seed_primary(seed_base, i, i / spp);
+    return IMBA_OK;
+}
+
+/* PT shading stage on an injected batch: sort by material, shade, compact -- the same kernels render() enqueues.
+ * Outputs: continuation queue (stable order), shadow queue (slot order, empty slots removed); contributions are added
+ * to the integrator's accumulation buffer. */
+extern "C" int imba_pt_shade_batch(imba_integrator* it, int count, const imba_ray* h_rays, const imba_hit* h_hits, const void* h_states,
+                                   imba_ray* h_rays_out, void* h_states_out, int* out_count, imba_ray* h_shadow_rays, void* h_shadow_states,
+                                   int* shadow_count) {
+    if (!it || count < 0 || count > it->capacity) { imba_set_error("batch larger than the integrator's queue capacity"); return IMBA_ERR_INVALID; }
+    const DeviceShading& S = *imba_shading_view(it->scene);
+    cudaStream_t st = it->stream;
+    IMBA_CUDA(cudaMemcpyAsync(it->rays[0], h_rays, (size_t)count * 32, cudaMemcpyHostToDevice, st), IMBA_ERR_CUDA);
+    IMBA_CUDA(cudaMemcpyAsync(it->hits, h_hits, (size_t)count * 16, cudaMemcpyHostToDevice, st), IMBA_ERR_CUDA);
+    IMBA_CUDA(cudaMemcpyAsync(it->states[0], h_states, (size_t)count * sizeof(PTState), cudaMemcpyHostToDevice, st), IMBA_ERR_CUDA);
+    IMBA_CUDA(cudaMemcpyAsync(it->count[0], &count, 4, cudaMemcpyHostToDevice, st), IMBA_ERR_CUDA);
+    IMBA_CUDA(imba_sort_hits_by_material(it->part, it->hits, S.indices, S.material_count, (int*)it->shadow_states, it->count[0], 0, count, st), IMBA_ERR_CUDA);
+    IMBA_CUDA(imba_pt_shade(S, it->rays[0], it->hits, (PTState*)it->states[0], it->part.indices, it->part.bin_start + S.material_count, it->count[0], count,
+                            it->shadow_rays, it->shadow_states, it->fb, it->cfg.max_path_len, it->d_stats, st), IMBA_ERR_CUDA);
+    // shadow queue: compact the valid slots (pixel_id >= 0) into rays[1] / states[1]
+    IMBA_CUDA(imba_compact_alive(it->part, nullptr, it->shadow_rays, it->shadow_states, sizeof(ShadowState), it->count[0], 0, count,
+                                 it->rays[1], it->states[1], it->count[1], st), IMBA_ERR_CUDA);
+    int nshadow = 0;
+    IMBA_CUDA(cudaMemcpyAsync(&nshadow, it->count[1], 4, cudaMemcpyDeviceToHost, st), IMBA_ERR_CUDA);
+    IMBA_CUDA(cudaStreamSynchronize(st), IMBA_ERR_CUDA);
+    if (count == 0) nshadow = 0;
+    IMBA_CUDA(cudaMemcpyAsync(h_shadow_rays, it->rays[1], (size_t)nshadow * 32, cudaMemcpyDeviceToHost, st), IMBA_ERR_CUDA);
+    IMBA_CUDA(cudaMemcpyAsync(h_shadow_states, it->states[1], (size_t)nshadow * sizeof(ShadowState), cudaMemcpyDeviceToHost, st), IMBA_ERR_CUDA);
+    IMBA_CUDA(cudaStreamSynchronize(st), IMBA_ERR_CUDA);
+    // continuation queue
+    IMBA_CUDA(imba_compact_alive(it->part, it->hits, it->rays[0], it->states[0], sizeof(PTState), it->count[0], 0, count,
+                                 it->rays[1], it->states[1], it->count[1], st), IMBA_ERR_CUDA);
+    int ncont = 0;
+    IMBA_CUDA(cudaMemcpyAsync(&ncont, it->count[1], 4, cudaMemcpyDeviceToHost, st), IMBA_ERR_CUDA);
+    IMBA_CUDA(cudaStreamSynchronize(st), IMBA_ERR_CUDA);
+    if (count == 0) ncont = 0;
+    IMBA_CUDA(cudaMemcpyAsync(h_rays_out, it->rays[1], (size_t)ncont * 32, cudaMemcpyDeviceToHost, st), IMBA_ERR_CUDA);
+    IMBA_CUDA(cudaMemcpyAsync(h_states_out, it->states[1], (size_t)ncont * sizeof(PTState), cudaMemcpyDeviceToHost, st), IMBA_ERR_CUDA);
+    IMBA_CUDA(cudaStreamSynchronize(st), IMBA_ERR_CUDA);
+    *out_count = ncont; *shadow_count = nshadow;
+    g_imba_launches.fetch_add(3 + 1 + 4 + 4);
+    return IMBA_OK;
+}
+
+/* ---- standalone queue primitives (ray_queue.h:161-244) on caller-owned device arrays -------------------------------- */
+extern "C" int imba_queue_sort_by_material(imba_scene* scene, const imba_hit* d_hits, int count, int* d_sorted_indices, int* d_hit_count, void* stream) {
+    if (!scene || !imba_shading_view(scene) || count < 0) { imba_set_error("invalid argument"); return IMBA_ERR_INVALID; }
+    const DeviceShading& S = *imba_shading_view(scene);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (count == 0) { IMBA_CUDA(cudaMemsetAsync(d_hit_count, 0, 4, st), IMBA_ERR_CUDA); IMBA_CUDA(cudaStreamSynchronize(st), IMBA_ERR_CUDA); return IMBA_OK; }
+    PartitionBuffers b;
+    IMBA_CUDA(imba_partition_alloc(b, count, S.material_count + 1), IMBA_ERR_CUDA);
+    cudaError_t e = imba_sort_hits_by_material(b, (const int4*)d_hits, S.indices, S.material_count, nullptr, nullptr, count, count, st);
+    if (e == cudaSuccess && count > 0) e = cudaMemcpyAsync(d_sorted_indices, b.indices, sizeof(int) * (size_t)count, cudaMemcpyDeviceToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_hit_count, b.bin_start + S.material_count, sizeof(int), cudaMemcpyDeviceToDevice, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    imba_partition_free(b);
+    g_imba_launches.fetch_add(3);
+    IMBA_CUDA(e, IMBA_ERR_CUDA);
+    return IMBA_OK;
+}
+
+extern "C" int imba_queue_compact_rays(const imba_ray* d_rays, const void* d_states, int state_bytes, imba_ray* d_rays_out, void* d_states_out,
+                                       int count, int* d_out_count, void* stream) {
+    if (count < 0 || state_bytes < 8 || state_bytes % 8) { imba_set_error("invalid argument (state size must be a multiple of 8)"); return IMBA_ERR_INVALID; }
+    cudaStream_t st = (cudaStream_t)stream;
+    if (count == 0) { IMBA_CUDA(cudaMemsetAsync(d_out_count, 0, 4, st), IMBA_ERR_CUDA); IMBA_CUDA(cudaStreamSynchronize(st), IMBA_ERR_CUDA); return IMBA_OK; }
+    PartitionBuffers b;
+    IMBA_CUDA(imba_partition_alloc(b, count, 2), IMBA_ERR_CUDA);
+    cudaError_t e = imba_compact_alive(b, nullptr, (const float4*)d_rays, d_states, state_bytes, nullptr, count, count, (float4*)d_rays_out, d_states_out, d_out_count, st);
+    if (e == cudaSuccess && count == 0) e = cudaMemsetAsync(d_out_count, 0, 4, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    imba_partition_free(b);
+    g_imba_launches.fetch_add(4);
+    IMBA_CUDA(e, IMBA_ERR_CUDA);
+    return IMBA_OK;
+}
+
+/* compact_hits (ray_queue.h:161-185): stable partition, hits first (material-sorted order is given by
+ * imba_queue_sort_by_material; this entry point physically permutes rays / hits / states like the reference does). */
+extern "C" int imba_queue_compact_hits(imba_scene* scene, const imba_ray* d_rays, const imba_hit* d_hits, const void* d_states, int state_bytes,
+                                       imba_ray* d_rays_out, imba_hit* d_hits_out, void* d_states_out, int count, int* d_hit_count, void* stream) {
+    if (!scene || !imba_shading_view(scene) || count < 0 || state_bytes < 8 || state_bytes % 8) { imba_set_error("invalid argument"); return IMBA_ERR_INVALID; }
+    const DeviceShading& S = *imba_shading_view(scene);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (count == 0) { IMBA_CUDA(cudaMemsetAsync(d_hit_count, 0, 4, st), IMBA_ERR_CUDA); IMBA_CUDA(cudaStreamSynchronize(st), IMBA_ERR_CUDA); return IMBA_OK; }
+    PartitionBuffers b;
+    IMBA_CUDA(imba_partition_alloc(b, count, 2), IMBA_ERR_CUDA);
+    // two bins: hit / miss  (material count 1 -> every hit falls into bin 0)
+    cudaError_t e = imba_sort_hits_by_material(b, (const int4*)d_hits, S.indices, 1, nullptr, nullptr, count, count, st);
+    if (e == cudaSuccess) e = imba_gather_queue(b.indices, nullptr, count, count, (const float4*)d_rays, (const int4*)d_hits, d_states, state_bytes,
+                                                (float4*)d_rays_out, (int4*)d_hits_out, d_states_out, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_hit_count, b.bin_start + 1, sizeof(int), cudaMemcpyDeviceToDevice, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    imba_partition_free(b);
+    g_imba_launches.fetch_add(4);
+    IMBA_CUDA(e, IMBA_ERR_CUDA);
+    return IMBA_OK;
+}

@@ -1,0 +1,57 @@
+/* integrator.cuh -- shared declarations of the device integrators (pt.cu, vcm.cu, integrator.cu). */
+#ifndef IMBA_INTEGRATOR_CUH
+#define IMBA_INTEGRATOR_CUH
+#include <algorithm>
+#include "api_common.h"
+#include "queue.cuh"
+#include "shade.cuh"
+
+/* PerspectiveCamera (render/ray_gen/camera.h:12-112) in closed form.  The reference builds 4x4 raster<->world
+ * matrices and inverts them numerically; the quirks are kept: aspect fixed at 1 (the image is stretched when
+ * width != height), raster y runs along cross(dir, right) (downwards), image-plane distance = width / (2 tan(fov/2)). */
+struct DevCamera {
+    float px, py, pz;       // position
+    float dx, dy, dz;       // forward (unit)
+    float rx, ry, rz;       // right = normalize(cross(dir, up))
+    float ux, uy, uz;       // cross(dir, right): raster +y
+    float tan_half;
+    int   width, height;
+    float img_plane_dist;
+    __host__ __device__ __forceinline__ V3 ray_dir(float sx, float sy) const {
+        const float a = (2.0f * sx / (float)width - 1.0f) * tan_half, b = (2.0f * sy / (float)height - 1.0f) * tan_half;
+        return normalize(v3(dx + a * rx + b * ux, dy + a * ry + b * uy, dz + a * rz + b * uz));
+    }
+    /* world_to_raster (camera.h:67-70); depth <= 0 means behind the camera */
+    __host__ __device__ __forceinline__ float2 to_raster(V3 p, float& depth) const {
+        const V3 d = v3(p.x - px, p.y - py, p.z - pz);
+        depth = d.x * dx + d.y * dy + d.z * dz;
+        const float a = (d.x * rx + d.y * ry + d.z * rz) / (depth * tan_half), b = (d.x * ux + d.y * uy + d.z * uz) / (depth * tan_half);
+        return make_float2((a + 1.0f) * 0.5f * (float)width, (b + 1.0f) * 0.5f * (float)height);
+    }
+};
+
+/* Seeding of a primary / light ray (ray_gen.h:57-72, 139-147): Bernstein hash of (seed_base, i) in 32-bit int
+ * arithmetic, RNG(seed) with the int sign-extended, then discard((seed % 5) + 16 + k % 5).  Returns the RNG state. */
+__host__ __device__ __forceinline__ uint64_t seed_primary(uint32_t seed_base, int i, int k) {
+    uint32_t seed = seed_base;
+    seed = (33u * seed) ^ (uint32_t)i; seed = (33u * seed) ^ (uint32_t)i; seed = (33u * seed) ^ (uint32_t)i; seed = (33u * seed) ^ (uint32_t)i;
+    const int s = (int)seed;
+    uint64_t state = (uint64_t)(int64_t)s;
+    const int n = (s % 5) + 16 + k % 5;
+    for (int j = 0; j < n; ++j) {
+        const uint32_t c = (uint32_t)(state >> 32), x = (uint32_t)(state & 0xffffffffu);
+        state = (uint64_t)x * 4294883355ull + c;
+    }
+    return state;
+}
+
+const DeviceShading* imba_shading_view(const imba_scene* s);
+
+cudaError_t imba_pt_raygen(const DevCamera& cam, int spp, uint32_t seed_base, int first, int count, float4* rays, PTState* states, int* count_out, cudaStream_t st);
+cudaError_t imba_pt_shade(const DeviceShading& S, float4* rays, const int4* hits, PTState* states, const int* sorted, const int* hit_count_ptr, const int* queue_count_ptr, int capacity,
+                          float4* shadow_rays, ShadowState* shadow_states, float* fb, int max_path_len, unsigned long long* ray_stats, cudaStream_t st);
+cudaError_t imba_probe_raygen(const DevCamera& cam, float4* rays, int count, cudaStream_t st);
+cudaError_t imba_probe_reduce(const float4* rays, const int4* hits, int quads, float* total, int* count, cudaStream_t st);
+cudaError_t imba_clear_shadow(ShadowState* s, int n, cudaStream_t st);
+
+#endif

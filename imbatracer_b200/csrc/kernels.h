@@ -14,6 +14,7 @@ struct TraceArgs {
     const float4*  rays;       // imba_ray[] as 2 x float4
     int4*          hits;       // imba_hit[]
     int            count;
+    const int*     count_ptr;  // if non-null the ray count is read from device memory (wavefront loops without host sync)
     unsigned*      counter;    // work counter, zero at launch
     uint32_t*      stats;      // 4 x u32 per ray or null
     // opacity masks (core/mask.h), only read by the MASKS instantiations
@@ -21,10 +22,14 @@ struct TraceArgs {
     const float2*  texcoords;
     const int*     masks;      // 3 ints per material
     const uint8_t* mask_buffer;
+    // mode 2 (any hit + resolve): ShadowState[] (16 bytes: pixel_id, r, g, b) and the W*H*3 accumulation buffer
+    const void*    shadow_states;
+    float*         framebuffer;
 };
 
 int         imba_trace_block_threads();
-int         imba_trace_blocks_per_sm(bool any_hit, bool masks, bool stats);
-cudaError_t imba_launch_trace(const TraceArgs& a, bool any_hit, bool masks, bool stats, int grid, cudaStream_t s);
+/* mode: 0 closest hit, 1 any hit, 2 any hit + shadow resolve */
+int         imba_trace_blocks_per_sm(int mode, bool masks, bool stats);
+cudaError_t imba_launch_trace(const TraceArgs& a, int mode, bool masks, bool stats, int grid, cudaStream_t s);
 
 #endif

@@ -68,8 +68,13 @@ __device__ __forceinline__ bool mask_opaque(const TraceArgs& P, int tri_id, floa
     return P.mask_buffer[mo + y * mw + x] != 0;
 }
 
-template <bool ANY, bool MASKS, bool STATS>
+/* MODE 0 = closest hit, 1 = any hit, 2 = any hit fused with process_shadow_rays (integrator.h:49-63): no hit record is
+ * written; an unoccluded ray adds its ShadowState throughput to the accumulation buffer; slots whose pixel_id < 0 are skipped. */
+template <int MODE, bool MASKS, bool STATS>
 __global__ void __launch_bounds__(BLOCK_THREADS) trace_kernel(const TraceArgs P) {
+    constexpr bool ANY = MODE != 0;
+    constexpr bool RESOLVE = MODE == 2;
+    const int ray_count = P.count_ptr ? *P.count_ptr : P.count;
     const unsigned lane = threadIdx.x & 31u;
     const uint4*  __restrict__ nodes = P.nodes;
     const float4* __restrict__ tris  = P.tris;
@@ -85,29 +90,31 @@ __global__ void __launch_bounds__(BLOCK_THREADS) trace_kernel(const TraceArgs P)
 
     for (;;) {
         // ---- refill idle lanes from the global work counter --------------------------------------
-        if (!exhausted) {
+        // (in resolve mode empty shadow slots are skipped, so a few rounds may be needed to fill the warp)
+        for (int round = 0; round < (RESOLVE ? 4 : 1) && !exhausted; ++round) {
             const unsigned need = __ballot_sync(FULL, !active);
-            if (need) {
-                const int leader = __ffs(need) - 1;
-                unsigned base = 0;
-                if ((int)lane == leader) base = atomicAdd(P.counter, (unsigned)__popc(need));
-                base = __shfl_sync(FULL, base, leader);
-                if (base + (unsigned)__popc(need) >= (unsigned)P.count) exhausted = true; // warp-uniform
-                if (!active) {
-                    const unsigned i = base + (unsigned)__popc(need & ((1u << lane) - 1u));
-                    if (i < (unsigned)P.count) {
-                        ray_idx = (int)i;
-                        const float4 o = __ldcs(P.rays + 2 * i), d = __ldcs(P.rays + 2 * i + 1);
-                        r.ox = o.x; r.oy = o.y; r.oz = o.z; r.dx = d.x; r.dy = d.y; r.dz = d.z; r.finish();
-                        tmin = o.w; tbest = d.w; ubest = 0.0f; tri_best = IMBA_NO_HIT; inst_best = IMBA_NO_HIT; cur_inst = -1;
-                        sp = 0; ngroup = make_uint2(P.top_root, 0x80000000u); tgroup = make_uint2(0, 0);
-                        if (STATS) { st_nodes = st_tris = st_insts = st_sp = 0; }
-                        active = true;
-                    }
+            if (!need) break;
+            const int leader = __ffs(need) - 1;
+            unsigned base = 0;
+            if ((int)lane == leader) base = atomicAdd(P.counter, (unsigned)__popc(need));
+            base = __shfl_sync(FULL, base, leader);
+            if (base + (unsigned)__popc(need) >= (unsigned)ray_count) exhausted = true; // warp-uniform
+            if (!active) {
+                const unsigned i = base + (unsigned)__popc(need & ((1u << lane) - 1u));
+                bool take = i < (unsigned)ray_count;
+                if (RESOLVE && take) take = __ldg(reinterpret_cast<const int*>(P.shadow_states) + 4 * i) >= 0;
+                if (take) {
+                    ray_idx = (int)i;
+                    const float4 o = __ldcs(P.rays + 2 * i), d = __ldcs(P.rays + 2 * i + 1);
+                    r.ox = o.x; r.oy = o.y; r.oz = o.z; r.dx = d.x; r.dy = d.y; r.dz = d.z; r.finish();
+                    tmin = o.w; tbest = d.w; ubest = 0.0f; tri_best = IMBA_NO_HIT; inst_best = IMBA_NO_HIT; cur_inst = -1;
+                    sp = 0; ngroup = make_uint2(P.top_root, 0x80000000u); tgroup = make_uint2(0, 0);
+                    if (STATS) { st_nodes = st_tris = st_insts = st_sp = 0; }
+                    active = true;
                 }
             }
         }
-        if (__ballot_sync(FULL, active) == 0) break;
+        if (__ballot_sync(FULL, active) == 0) { if (exhausted) break; continue; }
 
         // ---- traverse ----------------------------------------------------------------------------
         while (active) {
@@ -231,10 +238,18 @@ __global__ void __launch_bounds__(BLOCK_THREADS) trace_kernel(const TraceArgs P)
                 }
             }
             if (done) {
-                int4 h;
-                if (tri_best != IMBA_NO_HIT) h = make_int4(tri_best, inst_best, __float_as_int(tbest), __float_as_int(ubest));
-                else               h = make_int4(-1, -1, __float_as_int(tbest), 0);
-                __stcs(P.hits + ray_idx, h);
+                if (RESOLVE) {
+                    if (tri_best == IMBA_NO_HIT) {
+                        const float4 st = __ldg(reinterpret_cast<const float4*>(P.shadow_states) + ray_idx);
+                        float* px = P.framebuffer + 3 * (size_t)__float_as_int(st.x);
+                        atomicAdd(px, st.y); atomicAdd(px + 1, st.z); atomicAdd(px + 2, st.w);
+                    }
+                } else {
+                    int4 h;
+                    if (tri_best != IMBA_NO_HIT) h = make_int4(tri_best, inst_best, __float_as_int(tbest), __float_as_int(ubest));
+                    else               h = make_int4(-1, -1, __float_as_int(tbest), 0);
+                    __stcs(P.hits + ray_idx, h);
+                }
                 if (STATS) {
                     reinterpret_cast<uint4*>(P.stats)[ray_idx] = make_uint4(st_nodes, st_tris, st_insts, st_sp);
                 }
@@ -246,13 +261,13 @@ __global__ void __launch_bounds__(BLOCK_THREADS) trace_kernel(const TraceArgs P)
     }
 }
 
-template <bool ANY, bool MASKS, bool STATS>
+template <int ANY, bool MASKS, bool STATS>
 cudaError_t launch(const TraceArgs& a, int grid, cudaStream_t s) {
     trace_kernel<ANY, MASKS, STATS><<<grid, BLOCK_THREADS, 0, s>>>(a);
     return cudaGetLastError();
 }
 
-template <bool ANY, bool MASKS, bool STATS>
+template <int ANY, bool MASKS, bool STATS>
 int occupancy() {
     int n = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, trace_kernel<ANY, MASKS, STATS>, BLOCK_THREADS, 0);
@@ -263,18 +278,21 @@ int occupancy() {
 
 int imba_trace_block_threads() { return BLOCK_THREADS; }
 
-int imba_trace_blocks_per_sm(bool any_hit, bool masks, bool stats) {
-#define OCC(A, M, S) if (any_hit == A && masks == M && stats == S) return occupancy<A, M, S>();
-    OCC(false, false, false) OCC(false, false, true) OCC(false, true, false) OCC(false, true, true)
-    OCC(true, false, false) OCC(true, false, true) OCC(true, true, false) OCC(true, true, true)
+#define FOR_ALL_VARIANTS(X) \
+    X(0, false, false) X(0, false, true) X(0, true, false) X(0, true, true) \
+    X(1, false, false) X(1, false, true) X(1, true, false) X(1, true, true) \
+    X(2, false, false) X(2, true, false)
+
+int imba_trace_blocks_per_sm(int mode, bool masks, bool stats) {
+#define OCC(A, M, S) if (mode == A && masks == M && stats == S) return occupancy<A, M, S>();
+    FOR_ALL_VARIANTS(OCC)
 #undef OCC
     return 0;
 }
 
-cudaError_t imba_launch_trace(const TraceArgs& a, bool any_hit, bool masks, bool stats, int grid, cudaStream_t s) {
-#define RUN(A, M, S) if (any_hit == A && masks == M && stats == S) return launch<A, M, S>(a, grid, s);
-    RUN(false, false, false) RUN(false, false, true) RUN(false, true, false) RUN(false, true, true)
-    RUN(true, false, false) RUN(true, false, true) RUN(true, true, false) RUN(true, true, true)
+cudaError_t imba_launch_trace(const TraceArgs& a, int mode, bool masks, bool stats, int grid, cudaStream_t s) {
+#define RUN(A, M, S) if (mode == A && masks == M && stats == S) return launch<A, M, S>(a, grid, s);
+    FOR_ALL_VARIANTS(RUN)
 #undef RUN
     return cudaErrorInvalidValue;
 }

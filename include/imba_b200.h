@@ -212,6 +212,84 @@ void imba_bvh8_free(imba_bvh8* h);
 int  imba_bvh8_arrays(const imba_bvh8* h, const void** nodes, int64_t* node_count, const void** tris, int64_t* tri_count,
                       const void** insts, int64_t* inst_count, uint32_t* top_root, int32_t* max_depth);
 
+/* ------------------------------------------------------------------------------------------
+ * L2: ray-queue primitives on device arrays (render/scheduling/ray_queue.h:161-244)
+ * ---------------------------------------------------------------------------------------- */
+/* compact_hits (ray_queue.h:161-185): stable partition, hits first; rays/hits/states are permuted
+ * into the *_out arrays (ping-pong, no in-place swap).  Returns the hit count in *d_hit_count (device int). */
+int imba_queue_compact_hits(imba_scene* scene, const imba_ray* d_rays, const imba_hit* d_hits, const void* d_states,
+                            int state_bytes, imba_ray* d_rays_out, imba_hit* d_hits_out, void* d_states_out, int count,
+                            int* d_hit_count, void* stream);
+/* sort_by_material (ray_queue.h:211-244): fills d_sorted_indices[0..hit_count) with ray indices grouped by
+ * material id, stable within a material (the reference's scatter order is racy, any grouping is valid); misses of the
+ * `count` input hits are skipped (compact_hits is implied) and *d_hit_count (device int) receives the number of hits.
+ * All three queue calls are synchronous; state_bytes must be a multiple of 8 (16 / 40 / 48 in the reference). */
+int imba_queue_sort_by_material(imba_scene* scene, const imba_hit* d_hits, int count, int* d_sorted_indices,
+                                int* d_hit_count, void* stream);
+/* compact_rays (ray_queue.h:188-207): stable removal of states whose pixel_id (first int) is < 0. */
+int imba_queue_compact_rays(const imba_ray* d_rays, const void* d_states, int state_bytes, imba_ray* d_rays_out,
+                            void* d_states_out, int count, int* d_out_count, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * L2: integrators (render/integrators/{pt,vcm}.*) behind Integrator::{render,reset,preprocess,pixel_size}
+ * ---------------------------------------------------------------------------------------- */
+typedef enum { IMBA_ALGO_PT = 0, IMBA_ALGO_BPT = 1, IMBA_ALGO_VCM = 2, IMBA_ALGO_PPM = 3, IMBA_ALGO_VCM_PT = 4,
+               IMBA_ALGO_LT = 5 } imba_algorithm; /* frontend/cmd_line.h:38-45 */
+
+typedef struct {
+    int32_t algorithm;        /* imba_algorithm */
+    int32_t width, height;    /* -w -h (512x512) */
+    float   fov;              /* -f (60) */
+    float   cam_pos[3], cam_dir[3], cam_up[3];
+    int32_t spp;              /* --spp: samples per pixel within one iteration (1) */
+    int32_t max_path_len;     /* --max-path-len (10) */
+    int32_t light_path_count; /* --light-path-count (w*h/2) */
+    int32_t num_connections;  /* -c (1) */
+    int32_t num_knn;          /* -k (10) */
+    float   radius_factor;    /* -r (2) */
+    uint64_t seed;            /* replaces std::random_device (ray_gen.h:49-50) so runs are reproducible */
+    /* image-space sharding for multi-GPU: this rank renders sample slices
+     * iteration_index*rank_count + rank of the progressive sequence. */
+    int32_t rank, rank_count;
+} imba_render_settings;
+
+typedef struct imba_integrator imba_integrator;
+
+imba_integrator* imba_integrator_create(imba_scene* scene, const imba_render_settings* settings);
+void  imba_integrator_destroy(imba_integrator* it);
+/* Integrator::preprocess (integrator.cpp:14-71 pixel-size probe; light_vertices.cpp:15-129 cache sizing). */
+int   imba_integrator_preprocess(imba_integrator* it);
+float imba_integrator_pixel_size(const imba_integrator* it);
+/* Integrator::reset (vcm.h:69-72). */
+int   imba_integrator_reset(imba_integrator* it);
+/* Integrator::render: runs `iterations` progressive iterations, ADDING un-normalised radiance into the
+ * device accumulation buffer (the caller divides by iterations*spp, render_window.cpp:105,178). Asynchronous. */
+int   imba_integrator_render(imba_integrator* it, int iterations);
+/* Device pointer of the W*H*3 float accumulation buffer (for NCCL reduction by the host program). */
+float* imba_integrator_framebuffer(imba_integrator* it);
+/* Makes the integrator accumulate into a caller-owned device buffer (W*H*3 floats), e.g. one registered with NCCL. */
+int   imba_integrator_set_framebuffer(imba_integrator* it, float* d_rgb);
+/* The cudaStream_t all work of this integrator is enqueued on; imba_integrator_sync waits for it. */
+void* imba_integrator_stream(imba_integrator* it);
+int   imba_integrator_sync(imba_integrator* it);
+/* Synchronises and copies the accumulation buffer to host (W*H*3 floats). */
+int   imba_integrator_download(imba_integrator* it, float* h_rgb);
+int   imba_integrator_clear(imba_integrator* it);
+/* Ray statistics like TileScheduler's counters (tile_scheduler.h:59-60,117-127): out[0]=primary, out[1]=shadow rays. */
+int   imba_integrator_ray_counts(imba_integrator* it, uint64_t out[2]);
+
+/* PT shading stage on an injected batch (parity harness for calculate_intersection, integrator.h:71-123, and
+ * PathTracer::process_primary_rays, pt.cpp:82-160).  States are the reference's 40-byte PTState.
+ * Outputs: continuation rays/states (compacted, order = input order), shadow rays/states (16-byte ShadowState)
+ * and contributions added to the integrator's accumulation buffer.  Host pointers; synchronous. */
+/* Parity harnesses for PerspectiveCamera::generate_ray (camera.h:57-65) and the primary-ray seeding (ray_gen.h:57-72). */
+int imba_integrator_camera_rays(imba_integrator* it, int count, const float* raster_xy, imba_ray* h_rays);
+int imba_seed_states(uint32_t seed_base, int first, int count, int spp, uint64_t* out);
+
+int imba_pt_shade_batch(imba_integrator* it, int count, const imba_ray* h_rays, const imba_hit* h_hits,
+                        const void* h_states, imba_ray* h_rays_out, void* h_states_out, int* out_count,
+                        imba_ray* h_shadow_rays, void* h_shadow_states, int* shadow_count);
+
 #ifdef __cplusplus
 }
 #endif

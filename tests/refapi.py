@@ -163,3 +163,16 @@ class RefScene:
                                radius_factor, img.ctypes.data, stats.ctypes.data, C.byref(secs), C.byref(px))
         assert rc == 0
         return img, {"primary_rays": int(stats[0]), "shadow_rays": int(stats[1]), "seconds": secs.value, "pixel_size": px.value}
+
+    def pt_shade_batch(self, w, h, rays, hits, states, fov=60.0, max_path_len=10):
+        """PathTracer::process_primary_rays (pt.cpp:82-160) of the reference on an injected batch."""
+        n = len(rays)
+        rays_out = np.zeros(n, abi.RAY); states_out = np.zeros(n, abi.PT_STATE)
+        sh_rays = np.zeros(n, abi.RAY); sh_states = np.zeros(n, abi.SHADOW_STATE)
+        fb = np.zeros((h, w, 3), np.float32)
+        nc, ns = C.c_int(), C.c_int()
+        rc = self.L.ref_pt_shade_batch(self.h, w, h, fov, max_path_len, n, rays.ctypes.data, hits.ctypes.data, states.ctypes.data,
+                                       rays_out.ctypes.data, states_out.ctypes.data, C.addressof(nc), sh_rays.ctypes.data,
+                                       sh_states.ctypes.data, C.addressof(ns), fb.ctypes.data)
+        assert rc == 0
+        return rays_out[:nc.value], states_out[:nc.value], sh_rays[:ns.value], sh_states[:ns.value], fb

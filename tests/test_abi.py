@@ -45,3 +45,13 @@ def test_oracle_is_not_linked_into_the_product():
             if f.endswith((".py", ".cu", ".cpp", ".h")) :
                 text = open(os.path.join(root, f)).read()
                 assert "refapi" not in text and "liboracle" not in text, f
+
+
+def test_primary_ray_seeding_matches_reference_known_answers():
+    """ray_gen.h:57-72 (Bernstein hash in int arithmetic, sign-extended seed, discard count) -- host code, no GPU."""
+    import numpy as np
+    from tests.conftest import GOLDEN
+    k = np.load(os.path.join(GOLDEN, "rng_kat.npz"))
+    out = np.zeros(4096, np.uint64)
+    abi.check(abi.lib().imba_seed_states(0x1234ABCD, 0, 4096, 4, out.ctypes.data))
+    assert np.array_equal(out, k["seed_states"])
