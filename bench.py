@@ -188,6 +188,47 @@ def workload_config(flat, n):
             "parallelism": "independent ray queues per GPU, no collective"}
 
 
+def run_pt(scene, flat, rank, world, barrier, dist, iters, width=1920, height=1080):
+    import torch
+    from imbatracer_b200 import api
+    integ = api.Integrator(scene, api.render_settings(flat, "pt", width, height, spp=1, max_path_len=10, seed=0x1234ABCD, rank=rank, rank_count=world))
+    fb = torch.zeros(width * height * 3, dtype=torch.float32, device="cuda")
+    integ.set_framebuffer(fb)
+    integ.preprocess()
+    stream = torch.cuda.ExternalStream(integ.stream_ptr())
+    total = torch.zeros_like(fb)
+
+    def iteration():
+        integ.render(1)
+        if dist is not None:
+            with torch.cuda.stream(stream):
+                dist.all_reduce(fb)          # every rank ends up with the sum of all ranks' samples of this iteration
+        with torch.cuda.stream(stream):
+            total.add_(fb); fb.zero_()
+
+    for _ in range(2):
+        iteration()
+    integ.sync(); barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(iters):
+        iteration()
+    e1.record(stream)
+    integ.sync(); barrier()
+    ms = e0.elapsed_time(e1)
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t[0])
+    prim, shad = integ.ray_counts()
+    mean = float(total.mean()) / ((iters + 2) * world)
+    integ.close()
+    samples = width * height * iters * world
+    return {"workload": f"PT {width}x{height}, 1 spp per iteration per GPU, max path length 10, {SCENE}", "iterations": iters,
+            "samples_per_s": samples / (ms * 1e-3), "ms_per_iteration": ms / iters, "mrays_s_per_gpu": (prim + shad) / (iters + 2) * iters / (ms * 1e-3) / 1e6,
+            "framebuffer_allreduce_bytes": width * height * 12 if dist is not None else 0, "mean_radiance": mean}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -252,6 +293,8 @@ def run_ours(args):
         e2e_step()
     barrier()
     e2e_s = time.perf_counter() - t0
+    # configs[2]: PT 1920x1080 progressive, samples sharded over ranks, one NCCL sum of the float framebuffer per iteration
+    pt = run_pt(scene, flat, rank, world, barrier, dist if world > 1 else None, iters=max(4, min(args.steps * 2, 32)))
     sampler.stop_flag = True; sampler.join(timeout=2)
 
     t = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
@@ -284,6 +327,7 @@ def run_ours(args):
                         "steps": e2e_steps, "note": "imba_trace_host on pinned host queues, wall clock with device sync"},
                 "gpu_launches": int(launches),
                 "clocks": sampler.summary(),
+                "pt": pt,
                 "per_kernel": {name: {"ms": per_kernel_ms[i], "mrays_s": n / per_kernel_ms[i] / 1e3} for i, (name, _) in enumerate(BATCH_ORDER)},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                              "kernel": "trace_kernel<closest> on the incoherent batch", "peak_source": peak_src,
