@@ -114,7 +114,7 @@ int imba_scene_trace_ex(imba_scene* s, const TraceRequest& rq, cudaStream_t stre
     IMBA_CUDA(cudaMemsetAsync(ctr, 0, sizeof(unsigned), stream), IMBA_ERR_CUDA);
     TraceArgs a;
     a.nodes = s->d_nodes; a.tris = s->d_tris; a.insts = s->d_insts; a.top_root = s->top_root;
-    a.rays = (const float4*)rq.d_rays; a.hits = (int4*)rq.d_hits; a.count = rq.capacity; a.count_ptr = rq.d_count; a.counter = ctr; a.stats = rq.d_counters;
+    a.rays = (const float4*)rq.d_rays; a.hits = (int4*)rq.d_hits; a.count = rq.capacity; a.count_ptr = rq.d_count; a.count_mul = rq.count_mul; a.counter = ctr; a.stats = rq.d_counters;
     a.indices = s->d_mask_indices; a.texcoords = s->d_mask_texcoords; a.masks = s->d_masks; a.mask_buffer = s->d_mask_buffer;
     a.shadow_states = rq.d_shadow_states; a.framebuffer = rq.d_framebuffer;
     IMBA_CUDA(imba_launch_trace(a, rq.mode, masks, stats, grid, stream), IMBA_ERR_CUDA);

@@ -50,6 +50,7 @@ struct TraceRequest {
     const imba_ray* d_rays = nullptr; imba_hit* d_hits = nullptr;
     int capacity = 0;               // upper bound of the ray count (sizes the grid)
     const int* d_count = nullptr;   // optional device-resident ray count
+    int count_mul = 1;              // ray count = *d_count * count_mul
     int mode = 0;                   // 0 closest, 1 any hit, 2 any hit + shadow resolve
     uint32_t* d_counters = nullptr;
     const void* d_shadow_states = nullptr; float* d_framebuffer = nullptr;

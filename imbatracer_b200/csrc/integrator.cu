@@ -10,26 +10,6 @@
 #include "integrator.cuh"
 #include <cstring>
 
-struct imba_integrator {
-    imba_scene* scene = nullptr;
-    imba_render_settings cfg;
-    DevCamera cam;
-    cudaStream_t stream = nullptr;
-    int capacity = 0;
-    int state_bytes = sizeof(PTState);
-    float4* rays[2] = { nullptr, nullptr };
-    char*   states[2] = { nullptr, nullptr };
-    int*    count[2] = { nullptr, nullptr };
-    int4*   hits = nullptr;
-    float4* shadow_rays = nullptr; ShadowState* shadow_states = nullptr;
-    PartitionBuffers part;
-    float*  fb = nullptr; bool owns_fb = true;
-    unsigned long long* d_stats = nullptr;   // [0] primary rays, [1] shadow rays
-    float*  d_probe = nullptr;               // [0] total (float), [1] count (int)
-    uint64_t iteration = 0;
-    float   pixel_size = 1.0f;
-};
-
 static DevCamera make_camera(const imba_render_settings& s) {
     // CameraControl::setup (frontend/main.cpp:64-71) followed by PerspectiveCamera::move (camera.h:27-50), in double
     auto norm = [](double* v) { const double l = sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]); v[0] /= l; v[1] /= l; v[2] /= l; };
@@ -51,7 +31,7 @@ static DevCamera make_camera(const imba_render_settings& s) {
     return c;
 }
 
-static uint32_t iteration_seed(uint64_t seed, uint64_t global_iteration, uint32_t stream_id) {
+uint32_t imba_iteration_seed(uint64_t seed, uint64_t global_iteration, uint32_t stream_id) {
     // splitmix64 of (seed, iteration, stream): replaces std::random_device (ray_gen.h:49-50) so runs are reproducible
     uint64_t z = seed + 0x9E3779B97F4A7C15ull * (global_iteration * 4 + stream_id + 1);
     z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull; z = (z ^ (z >> 27)) * 0x94D049BB133111EBull; z ^= z >> 31;
@@ -65,6 +45,7 @@ extern "C" void imba_integrator_destroy(imba_integrator* it) {
     imba_partition_free(it->part);
     if (it->owns_fb) cudaFree(it->fb);
     cudaFree(it->d_stats); cudaFree(it->d_probe);
+    imba_vcm_free(it);
     if (it->stream) cudaStreamDestroy(it->stream);
     delete it;
 }
@@ -72,14 +53,19 @@ extern "C" void imba_integrator_destroy(imba_integrator* it) {
 extern "C" imba_integrator* imba_integrator_create(imba_scene* scene, const imba_render_settings* s) {
     if (!scene || !s || !imba_shading_view(scene)) { imba_set_error("integrator needs a scene created with geometry, materials and lights"); return nullptr; }
     if (s->width <= 0 || s->height <= 0 || s->spp <= 0 || s->max_path_len <= 0) { imba_set_error("invalid render settings"); return nullptr; }
-    if (s->algorithm != IMBA_ALGO_PT) { imba_set_error("algorithm %d is not available on the device yet (PT only)", s->algorithm); return nullptr; }
+    if (s->algorithm < IMBA_ALGO_PT || s->algorithm > IMBA_ALGO_LT) { imba_set_error("unknown algorithm %d", s->algorithm); return nullptr; }
+    const bool vcm = s->algorithm != IMBA_ALGO_PT;
+    if (vcm && (s->light_path_count <= 0 || s->num_connections < 1 || s->num_knn < 1 || s->num_knn > 32)) { imba_set_error("invalid VCM settings (light paths > 0, connections >= 1, 1 <= knn <= 32)"); return nullptr; }
     if (imba_shading_view(scene)->light_count <= 0) { imba_set_error("scene has no lights"); return nullptr; }
     if (imba_shading_view(scene)->material_count > 1023) { imba_set_error("more than 1023 materials"); return nullptr; }
     imba_integrator* it = new imba_integrator;
     it->scene = scene; it->cfg = *s; it->cam = make_camera(*s);
     if (it->cfg.rank_count <= 0) { it->cfg.rank_count = 1; it->cfg.rank = 0; }
-    const long long cap = (long long)s->width * s->height * s->spp;
-    if (cap > (1ll << 30)) { imba_set_error("queue capacity too large"); delete it; return nullptr; }
+    it->pixel_capacity = s->width * s->height * s->spp;
+    it->state_bytes = vcm ? (int)sizeof(VCMState) : (int)sizeof(PTState);
+    it->shadow_slots = vcm ? s->num_connections + 1 : 1;
+    const long long cap = std::max((long long)s->width * s->height * s->spp, vcm ? (long long)s->light_path_count : 0ll);
+    if (cap * it->shadow_slots > (1ll << 30)) { imba_set_error("queue capacity too large"); delete it; return nullptr; }
     it->capacity = (int)cap;
     bool ok = cudaStreamCreateWithFlags(&it->stream, cudaStreamNonBlocking) == cudaSuccess;
     for (int i = 0; i < 2 && ok; ++i) {
@@ -88,8 +74,8 @@ extern "C" imba_integrator* imba_integrator_create(imba_scene* scene, const imba
         ok = ok && cudaMalloc((void**)&it->count[i], 16) == cudaSuccess;
     }
     ok = ok && cudaMalloc((void**)&it->hits, (size_t)cap * 16) == cudaSuccess;
-    ok = ok && cudaMalloc((void**)&it->shadow_rays, (size_t)cap * 32) == cudaSuccess;
-    ok = ok && cudaMalloc((void**)&it->shadow_states, (size_t)cap * 16) == cudaSuccess;
+    ok = ok && cudaMalloc((void**)&it->shadow_rays, (size_t)cap * it->shadow_slots * 32) == cudaSuccess;
+    ok = ok && cudaMalloc((void**)&it->shadow_states, (size_t)cap * it->shadow_slots * 16) == cudaSuccess;
     ok = ok && imba_partition_alloc(it->part, it->capacity, imba_shading_view(scene)->material_count + 1) == cudaSuccess;
     ok = ok && cudaMalloc((void**)&it->fb, (size_t)s->width * s->height * 3 * sizeof(float)) == cudaSuccess;
     ok = ok && cudaMalloc((void**)&it->d_stats, 16) == cudaSuccess && cudaMalloc((void**)&it->d_probe, 16) == cudaSuccess;
@@ -110,7 +96,7 @@ extern "C" void* imba_integrator_stream(imba_integrator* it) { return it ? (void
 extern "C" int imba_integrator_preprocess(imba_integrator* it) {
     if (!it) { imba_set_error("null argument"); return IMBA_ERR_INVALID; }
     const int quads = ((it->cam.width + 7) / 8) * ((it->cam.height + 7) / 8);
-    const int n = std::min(quads * 4, it->capacity / 4 * 4);
+    const int n = std::min(quads * 4, it->capacity / 4 * 4); // capacity >= width * height >= 4 * quads
     IMBA_CUDA(cudaMemsetAsync(it->d_probe, 0, 16, it->stream), IMBA_ERR_CUDA);
     IMBA_CUDA(imba_probe_raygen(it->cam, it->rays[0], n, it->stream), IMBA_ERR_CUDA);
     int rc = imba_scene_trace(it->scene, (const imba_ray*)it->rays[0], (imba_hit*)it->hits, n, 0, nullptr, it->stream);
@@ -121,6 +107,7 @@ extern "C" int imba_integrator_preprocess(imba_integrator* it) {
     IMBA_CUDA(cudaStreamSynchronize(it->stream), IMBA_ERR_CUDA);
     int cnt; memcpy(&cnt, &h[1], 4);
     it->pixel_size = cnt == 0 ? 1.0f : h[0] / (float)cnt;
+    if (it->cfg.algorithm != IMBA_ALGO_PT) return imba_vcm_preprocess(it);
     return IMBA_OK;
 }
 
@@ -132,7 +119,7 @@ static int pt_wavefront(imba_integrator* it, int cur, int capacity) {
     TraceRequest rq; rq.d_rays = (const imba_ray*)it->rays[cur]; rq.d_hits = (imba_hit*)it->hits; rq.capacity = capacity; rq.d_count = it->count[cur]; rq.mode = 0;
     int rc = imba_scene_trace_ex(it->scene, rq, it->stream);
     if (rc != IMBA_OK) return rc;
-    IMBA_CUDA(imba_sort_hits_by_material(it->part, it->hits, S.indices, S.material_count, (int*)it->shadow_states, it->count[cur], 0, capacity, it->stream), IMBA_ERR_CUDA);
+    IMBA_CUDA(imba_sort_hits_by_material(it->part, it->hits, S.indices, S.material_count, (int*)it->shadow_states, 1, it->count[cur], 0, capacity, it->stream), IMBA_ERR_CUDA);
     IMBA_CUDA(imba_pt_shade(S, it->rays[cur], it->hits, (PTState*)it->states[cur], it->part.indices, it->part.bin_start + S.material_count, it->count[cur], capacity,
                             it->shadow_rays, it->shadow_states, it->fb, it->cfg.max_path_len, it->d_stats, it->stream), IMBA_ERR_CUDA);
     TraceRequest sq; sq.d_rays = (const imba_ray*)it->shadow_rays; sq.capacity = capacity; sq.d_count = it->count[cur]; sq.mode = 2;
@@ -148,8 +135,13 @@ static int pt_wavefront(imba_integrator* it, int cur, int capacity) {
 extern "C" int imba_integrator_render(imba_integrator* it, int iterations) {
     if (!it || iterations < 0) { imba_set_error("invalid argument"); return IMBA_ERR_INVALID; }
     for (int k = 0; k < iterations; ++k, ++it->iteration) {
+        if (it->cfg.algorithm != IMBA_ALGO_PT) {
+            const int rc = imba_vcm_render_iteration(it);
+            if (rc != IMBA_OK) return rc;
+            continue;
+        }
         const uint64_t global_iter = it->iteration * (uint64_t)it->cfg.rank_count + (uint64_t)it->cfg.rank;
-        const uint32_t seed_base = iteration_seed(it->cfg.seed, global_iter, 0);
+        const uint32_t seed_base = imba_iteration_seed(it->cfg.seed, global_iter, 0);
         IMBA_CUDA(imba_pt_raygen(it->cam, it->cfg.spp, seed_base, 0, it->capacity, it->rays[0], (PTState*)it->states[0], it->count[0], it->stream), IMBA_ERR_CUDA);
         g_imba_launches.fetch_add(1);
         int cur = 0;
@@ -216,14 +208,14 @@ extern "C" int imba_seed_states(uint32_t seed_base, int first, int count, int sp
 extern "C" int imba_pt_shade_batch(imba_integrator* it, int count, const imba_ray* h_rays, const imba_hit* h_hits, const void* h_states,
                                    imba_ray* h_rays_out, void* h_states_out, int* out_count, imba_ray* h_shadow_rays, void* h_shadow_states,
                                    int* shadow_count) {
-    if (!it || count < 0 || count > it->capacity) { imba_set_error("batch larger than the integrator's queue capacity"); return IMBA_ERR_INVALID; }
+    if (!it || count < 0 || count > it->capacity || it->cfg.algorithm != IMBA_ALGO_PT) { imba_set_error("needs a PT integrator whose queue capacity covers the batch"); return IMBA_ERR_INVALID; }
     const DeviceShading& S = *imba_shading_view(it->scene);
     cudaStream_t st = it->stream;
     IMBA_CUDA(cudaMemcpyAsync(it->rays[0], h_rays, (size_t)count * 32, cudaMemcpyHostToDevice, st), IMBA_ERR_CUDA);
     IMBA_CUDA(cudaMemcpyAsync(it->hits, h_hits, (size_t)count * 16, cudaMemcpyHostToDevice, st), IMBA_ERR_CUDA);
     IMBA_CUDA(cudaMemcpyAsync(it->states[0], h_states, (size_t)count * sizeof(PTState), cudaMemcpyHostToDevice, st), IMBA_ERR_CUDA);
     IMBA_CUDA(cudaMemcpyAsync(it->count[0], &count, 4, cudaMemcpyHostToDevice, st), IMBA_ERR_CUDA);
-    IMBA_CUDA(imba_sort_hits_by_material(it->part, it->hits, S.indices, S.material_count, (int*)it->shadow_states, it->count[0], 0, count, st), IMBA_ERR_CUDA);
+    IMBA_CUDA(imba_sort_hits_by_material(it->part, it->hits, S.indices, S.material_count, (int*)it->shadow_states, 1, it->count[0], 0, count, st), IMBA_ERR_CUDA);
     IMBA_CUDA(imba_pt_shade(S, it->rays[0], it->hits, (PTState*)it->states[0], it->part.indices, it->part.bin_start + S.material_count, it->count[0], count,
                             it->shadow_rays, it->shadow_states, it->fb, it->cfg.max_path_len, it->d_stats, st), IMBA_ERR_CUDA);
     // shadow queue: compact the valid slots (pixel_id >= 0) into rays[1] / states[1]
@@ -259,7 +251,7 @@ extern "C" int imba_queue_sort_by_material(imba_scene* scene, const imba_hit* d_
     if (count == 0) { IMBA_CUDA(cudaMemsetAsync(d_hit_count, 0, 4, st), IMBA_ERR_CUDA); IMBA_CUDA(cudaStreamSynchronize(st), IMBA_ERR_CUDA); return IMBA_OK; }
     PartitionBuffers b;
     IMBA_CUDA(imba_partition_alloc(b, count, S.material_count + 1), IMBA_ERR_CUDA);
-    cudaError_t e = imba_sort_hits_by_material(b, (const int4*)d_hits, S.indices, S.material_count, nullptr, nullptr, count, count, st);
+    cudaError_t e = imba_sort_hits_by_material(b, (const int4*)d_hits, S.indices, S.material_count, nullptr, 1, nullptr, count, count, st);
     if (e == cudaSuccess && count > 0) e = cudaMemcpyAsync(d_sorted_indices, b.indices, sizeof(int) * (size_t)count, cudaMemcpyDeviceToDevice, st);
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_hit_count, b.bin_start + S.material_count, sizeof(int), cudaMemcpyDeviceToDevice, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
@@ -296,7 +288,7 @@ extern "C" int imba_queue_compact_hits(imba_scene* scene, const imba_ray* d_rays
     PartitionBuffers b;
     IMBA_CUDA(imba_partition_alloc(b, count, 2), IMBA_ERR_CUDA);
     // two bins: hit / miss  (material count 1 -> every hit falls into bin 0)
-    cudaError_t e = imba_sort_hits_by_material(b, (const int4*)d_hits, S.indices, 1, nullptr, nullptr, count, count, st);
+    cudaError_t e = imba_sort_hits_by_material(b, (const int4*)d_hits, S.indices, 1, nullptr, 1, nullptr, count, count, st);
     if (e == cudaSuccess) e = imba_gather_queue(b.indices, nullptr, count, count, (const float4*)d_rays, (const int4*)d_hits, d_states, state_bytes,
                                                 (float4*)d_rays_out, (int4*)d_hits_out, d_states_out, st);
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_hit_count, b.bin_start + 1, sizeof(int), cudaMemcpyDeviceToDevice, st);

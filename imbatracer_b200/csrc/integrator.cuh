@@ -47,6 +47,41 @@ __host__ __device__ __forceinline__ uint64_t seed_primary(uint32_t seed_base, in
 
 const DeviceShading* imba_shading_view(const imba_scene* s);
 
+struct imba_integrator {
+    imba_scene* scene = nullptr;
+    imba_render_settings cfg;
+    DevCamera cam;
+    cudaStream_t stream = nullptr;
+    int capacity = 0;
+    int state_bytes = sizeof(PTState);
+    float4* rays[2] = { nullptr, nullptr };
+    char*   states[2] = { nullptr, nullptr };
+    int*    count[2] = { nullptr, nullptr };
+    int4*   hits = nullptr;
+    float4* shadow_rays = nullptr; ShadowState* shadow_states = nullptr;
+    PartitionBuffers part;
+    float*  fb = nullptr; bool owns_fb = true;
+    unsigned long long* d_stats = nullptr;   // [0] primary rays, [1] shadow rays
+    float*  d_probe = nullptr;               // [0] total (float), [1] count (int)
+    uint64_t iteration = 0;
+    float   pixel_size = 1.0f;
+    // VCM family (vcm_host.cu)
+    int     shadow_slots = 1;                // num_connections + 1 shadow rays per camera vertex (frontend/main.cpp:132)
+    int     pixel_capacity = 0;              // width * height * spp
+    struct DevLightVertex* cache = nullptr; int cache_capacity = 0; int* cache_last = nullptr;
+    struct GridParams* grid = nullptr; int* grid_bbox = nullptr; int* cells = nullptr; unsigned table = 0; int* block_sums = nullptr;
+    struct DevPhoton* photons = nullptr;
+    float   base_radius = 0.0f;
+};
+int imba_vcm_allocate(imba_integrator* it);
+void imba_vcm_free(imba_integrator* it);
+int imba_vcm_preprocess(imba_integrator* it);
+int imba_vcm_render_iteration(imba_integrator* it);
+uint32_t imba_iteration_seed(uint64_t seed, uint64_t global_iteration, uint32_t stream_id);
+
+
+
+
 cudaError_t imba_pt_raygen(const DevCamera& cam, int spp, uint32_t seed_base, int first, int count, float4* rays, PTState* states, int* count_out, cudaStream_t st);
 cudaError_t imba_pt_shade(const DeviceShading& S, float4* rays, const int4* hits, PTState* states, const int* sorted, const int* hit_count_ptr, const int* queue_count_ptr, int capacity,
                           float4* shadow_rays, ShadowState* shadow_states, float* fb, int max_path_len, unsigned long long* ray_stats, cudaStream_t st);

@@ -15,6 +15,7 @@ struct TraceArgs {
     int4*          hits;       // imba_hit[]
     int            count;
     const int*     count_ptr;  // if non-null the ray count is read from device memory (wavefront loops without host sync)
+    int            count_mul;  // ray count = *count_ptr * count_mul (several shadow slots per queue entry)
     unsigned*      counter;    // work counter, zero at launch
     uint32_t*      stats;      // 4 x u32 per ray or null
     // opacity masks (core/mask.h), only read by the MASKS instantiations

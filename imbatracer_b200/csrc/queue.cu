@@ -19,10 +19,10 @@ namespace {
 constexpr unsigned FULL = 0xffffffffu;
 
 struct HitMaterialKey {   // compact_hits + sort_by_material: key = material id, misses go to the last bin
-    const int4* hits; const int4* indices; int nmat; int* shadow_pixel; // shadow_pixel: optional, stride 4 ints
+    const int4* hits; const int4* indices; int nmat; int* shadow_pixel; int shadow_slots; // shadow_pixel: optional, stride 4 ints
     __device__ __forceinline__ int operator()(int i) const {
         const int tri = __ldg(&hits[i].x);
-        if (shadow_pixel) shadow_pixel[4 * i] = -1; // no shadow ray in this slot until the shading kernel writes one
+        if (shadow_pixel) for (int k = 0; k < shadow_slots; ++k) shadow_pixel[4 * ((size_t)i * shadow_slots + k)] = -1; // no shadow rays yet
         if (tri < 0) return nmat;
         const int m = __ldg(&indices[tri].w);
         return m < 0 ? 0 : (m >= nmat ? nmat - 1 : m);
@@ -178,9 +178,9 @@ void imba_partition_free(PartitionBuffers& b) {
     b = PartitionBuffers();
 }
 
-cudaError_t imba_sort_hits_by_material(const PartitionBuffers& b, const int4* hits, const int4* indices, int nmat, int* shadow_pixel,
+cudaError_t imba_sort_hits_by_material(const PartitionBuffers& b, const int4* hits, const int4* indices, int nmat, int* shadow_pixel, int shadow_slots,
                                        const int* count_ptr, int count_imm, int capacity, cudaStream_t st) {
-    return run_partition(b, HitMaterialKey{ hits, indices, nmat, shadow_pixel }, count_ptr, count_imm, capacity, nmat + 1, st);
+    return run_partition(b, HitMaterialKey{ hits, indices, nmat, shadow_pixel, shadow_slots }, count_ptr, count_imm, capacity, nmat + 1, st);
 }
 
 cudaError_t imba_compact_alive(const PartitionBuffers& b, const int4* hits, const float4* rays, const void* states, int state_bytes,

@@ -164,6 +164,7 @@ struct Bsdf {
                   v_tangent.z * d.x + u_tangent.z * d.y + normal.z * d.z);
     }
     __device__ __forceinline__ bool has_btdf() const { return kind == MAT_GLASS; }
+    __device__ __forceinline__ bool is_specular() const { return kind == MAT_MIRROR || kind == MAT_GLASS; } // Material::is_specular
     __device__ __forceinline__ int brdf_flags() const {
         return kind == MAT_DIFFUSE ? (BSDF_DIFFUSE | BSDF_REFLECTION)
              : kind == MAT_GLOSSY  ? (BSDF_GLOSSY | BSDF_DIFFUSE | BSDF_REFLECTION) : (BSDF_SPECULAR | BSDF_REFLECTION);
@@ -254,8 +255,10 @@ struct Bsdf {
         const float factor = adjoint ? 1.0f : sqr(eta_in / eta_trans);
         return factor * (1.0f - fr) * tf / fabsf(i.z);
     }
-    /* bsdf.h:149-204 with flags = BSDF_ALL */
-    __device__ __forceinline__ V3 sample(V3 out_dir, V3& in_dir, Rng& rng, int& sampled_flags, float& pdf_out) const {
+    /* bsdf.h:149-204 with flags = BSDF_ALL, or (specular_only) SPECULAR | REFLECTION | TRANSMISSION as the PPM camera
+     * pass requests (vcm.cpp:141-143): non-specular BRDFs then do not match and nothing is drawn from the RNG */
+    __device__ __forceinline__ V3 sample(V3 out_dir, V3& in_dir, Rng& rng, int& sampled_flags, float& pdf_out, bool specular_only = false) const {
+        if (specular_only && (kind == MAT_DIFFUSE || kind == MAT_GLOSSY)) { pdf_out = 0.0f; sampled_flags = 0; return v3(0.0f); }
         const V3 lo = to_local(out_dir);
         const float btdf_prob = has_btdf() ? 1.0f - fresnel_dielectric_eval(lo.z, 1.0f, eta) : 0.0f;
         const float rnd = rng.uniform();
@@ -415,6 +418,25 @@ struct PTState {     // 40 bytes, layout of the reference's struct
     float last_pdf; uint32_t pad;
 };
 struct ShadowState { int pixel_id; float r, g, b; }; // 16 bytes
+struct VCMState {    // 48 bytes (render/integrators/vcm.h:26-36)
+    int pixel_id; int light_id; uint64_t rng;
+    float tr, tg, tb;
+    uint32_t len_finite; // path_length : 31, finite_light : 1
+    float dVC, dVCM, dVM; uint32_t pad;
+};
+static_assert(sizeof(VCMState) == 48, "state layouts");
+/* LightPathVertex (light_vertices.h:15-35) packed to 7 x float4 */
+struct DevLightVertex {
+    float4 pos_len;   // position, path_length (int bits)
+    float4 out_mat;   // out_dir, material id (int bits)
+    float4 n_dvc;     // shading normal, dVC
+    float4 gn_dvcm;   // geometric normal, dVCM
+    float4 ut_dvm;    // u_tangent, dVM
+    float4 vt_u;      // v_tangent, uv.x
+    float4 thr_v;     // throughput, uv.y
+};
+/* VCMPhoton (light_vertices.h:39-56) padded to 3 x float4 */
+struct DevPhoton { float4 pos_dvcm; float4 dir_dvm; float4 thr; };
 static_assert(sizeof(PTState) == 40 && sizeof(ShadowState) == 16, "state layouts");
 
 #endif

@@ -74,7 +74,7 @@ template <int MODE, bool MASKS, bool STATS>
 __global__ void __launch_bounds__(BLOCK_THREADS) trace_kernel(const TraceArgs P) {
     constexpr bool ANY = MODE != 0;
     constexpr bool RESOLVE = MODE == 2;
-    const int ray_count = P.count_ptr ? *P.count_ptr : P.count;
+    const int ray_count = P.count_ptr ? *P.count_ptr * P.count_mul : P.count;
     const unsigned lane = threadIdx.x & 31u;
     const uint4*  __restrict__ nodes = P.nodes;
     const float4* __restrict__ tris  = P.tris;

@@ -1,0 +1,32 @@
+/* vcm.cuh -- parameters shared by the VCM kernels (vcm.cu) and their host driver (integrator.cu). */
+#ifndef IMBA_VCM_CUH
+#define IMBA_VCM_CUH
+#include "integrator.cuh"
+
+#define IMBA_MAX_KNN 32
+
+struct VcmParams {            // per-iteration constants of VCMIntegrator::render (vcm.cpp:26-46)
+    float pm_radius, base_radius, mis_eta_vc, mis_eta_vm;
+    int   light_path_count, num_connections, num_knn, max_path_len;
+};
+struct GridParams {           // HashGrid members (rangesearch.h:148-156) + the vertex count of the iteration
+    float lo[3], hi[3];
+    float radius_sqr, inv_cell_size;
+    int   count;
+};
+struct VcmLaunch {
+    const DeviceShading* S; VcmParams P; DevCamera cam;
+    float4* rays; const int4* hits; VCMState* states; const int* sorted; const int* hit_count_ptr; const int* queue_count_ptr; int capacity;
+    float4* shadow_rays; ShadowState* shadow_states;
+    DevLightVertex* cache; int cache_capacity; int* cache_last;
+    const GridParams* grid; const int* cells; unsigned table; const DevPhoton* photons;
+    float* fb; unsigned long long* ray_stats;
+};
+
+cudaError_t imba_vcm_light_raygen(const DeviceShading& S, const VcmParams& P, uint32_t seed_base, int count, float4* rays, VCMState* states, int* count_out, cudaStream_t st);
+cudaError_t imba_vcm_camera_raygen(const DevCamera& cam, const VcmParams& P, int spp, uint32_t seed_base, int count, float4* rays, VCMState* states, int* count_out, cudaStream_t st);
+cudaError_t imba_vcm_light_shade(int algo, const VcmLaunch& a, cudaStream_t st);
+cudaError_t imba_vcm_camera_shade(int algo, const VcmLaunch& a, cudaStream_t st);
+cudaError_t imba_grid_build(const DevLightVertex* cache, const int* cache_last, int cache_capacity, float radius, GridParams* grid, int* bbox, int* cells, unsigned table,
+                            int* block_sums, DevPhoton* photons, bool build_cells, cudaStream_t st);
+#endif

@@ -1,0 +1,161 @@
+/* vcm_host.cu -- host driver of the VCM family on the device: VCMIntegrator::{preprocess, render, trace_light_paths,
+ * trace_camera_paths} (vcm.h:74-81, vcm.cpp:26-130) and LightVertices::{compute_cache_size, build, clear}
+ * (light_vertices.cpp:15-129, light_vertices.h:70-116).
+ *
+ * Light pass: ONE wavefront over all light paths (the reference tiles them per light, tile_gen.h:102-177); light paths
+ * have no length cap (only Russian roulette ends them, vcm.cpp:133-139), so the host reads the queue size back after
+ * every wavefront of the light pass.  The camera pass is capped by max_path_len and is enqueued without host sync.
+ */
+#include "vcm.cuh"
+
+static VcmParams iteration_params(const imba_integrator* it, uint64_t iteration_1based) {
+    // vcm.cpp:28-46
+    const float radius_alpha = 0.75f;
+    VcmParams P;
+    P.base_radius = it->base_radius;
+    P.pm_radius = it->base_radius / powf((float)iteration_1based, 0.5f * (1.0f - radius_alpha));
+    P.pm_radius = std::max(P.pm_radius, 1e-7f);
+    const float eta_vcm = IMBA_PI * sqr(P.pm_radius) * it->cfg.light_path_count;
+    P.mis_eta_vc = 1.0f / eta_vcm;
+    P.mis_eta_vm = it->cfg.algorithm == IMBA_ALGO_BPT ? 0.0f : eta_vcm;
+    P.light_path_count = it->cfg.light_path_count; P.num_connections = it->cfg.num_connections; P.num_knn = it->cfg.num_knn;
+    P.max_path_len = it->cfg.max_path_len;
+    return P;
+}
+
+static VcmLaunch base_launch(imba_integrator* it, const VcmParams& P, int cur, int capacity) {
+    const DeviceShading* S = imba_shading_view(it->scene);
+    VcmLaunch a;
+    a.S = S; a.P = P; a.cam = it->cam;
+    a.rays = it->rays[cur]; a.hits = it->hits; a.states = (VCMState*)it->states[cur]; a.sorted = it->part.indices;
+    a.hit_count_ptr = it->part.bin_start + S->material_count; a.queue_count_ptr = it->count[cur]; a.capacity = capacity;
+    a.shadow_rays = it->shadow_rays; a.shadow_states = it->shadow_states;
+    a.cache = it->cache; a.cache_capacity = it->cache_capacity; a.cache_last = it->cache_last;
+    a.grid = it->grid; a.cells = it->cells; a.table = it->table; a.photons = it->photons;
+    a.fb = it->fb; a.ray_stats = it->d_stats;
+    return a;
+}
+
+/* One wavefront of the light pass (light != 0) or of the camera pass. */
+static int vcm_wavefront(imba_integrator* it, const VcmParams& P, int algo, bool light, int cur, int capacity) {
+    const DeviceShading& S = *imba_shading_view(it->scene);
+    const int slots = light ? 1 : it->shadow_slots;
+    TraceRequest rq; rq.d_rays = (const imba_ray*)it->rays[cur]; rq.d_hits = (imba_hit*)it->hits; rq.capacity = capacity; rq.d_count = it->count[cur]; rq.mode = 0;
+    int rc = imba_scene_trace_ex(it->scene, rq, it->stream);
+    if (rc != IMBA_OK) return rc;
+    IMBA_CUDA(imba_sort_hits_by_material(it->part, it->hits, S.indices, S.material_count, (int*)it->shadow_states, slots, it->count[cur], 0, capacity, it->stream), IMBA_ERR_CUDA);
+    const VcmLaunch a = base_launch(it, P, cur, capacity);
+    IMBA_CUDA(light ? imba_vcm_light_shade(algo, a, it->stream) : imba_vcm_camera_shade(algo, a, it->stream), IMBA_ERR_CUDA);
+    const bool shadows = light ? algo != IMBA_ALGO_PPM : algo != IMBA_ALGO_PPM; // PPM emits no shadow rays in either pass
+    if (shadows) {
+        TraceRequest sq; sq.d_rays = (const imba_ray*)it->shadow_rays; sq.capacity = capacity * slots; sq.d_count = it->count[cur]; sq.count_mul = slots; sq.mode = 2;
+        sq.d_shadow_states = it->shadow_states; sq.d_framebuffer = it->fb;
+        rc = imba_scene_trace_ex(it->scene, sq, it->stream);
+        if (rc != IMBA_OK) return rc;
+    }
+    IMBA_CUDA(imba_compact_alive(it->part, it->hits, it->rays[cur], it->states[cur], it->state_bytes, it->count[cur], 0, capacity,
+                                 it->rays[cur ^ 1], it->states[cur ^ 1], it->count[cur ^ 1], it->stream), IMBA_ERR_CUDA);
+    g_imba_launches.fetch_add(3 + 1 + 4 + (shadows ? 1 : 0));
+    return IMBA_OK;
+}
+
+/* Traces all light paths of one iteration; returns the number of wavefronts through *waves. */
+static int light_pass(imba_integrator* it, const VcmParams& P, int algo, uint32_t seed_base, int path_count, int* waves) {
+    const DeviceShading& S = *imba_shading_view(it->scene);
+    IMBA_CUDA(cudaMemsetAsync(it->cache_last, 0, sizeof(int), it->stream), IMBA_ERR_CUDA);
+    IMBA_CUDA(imba_vcm_light_raygen(S, P, seed_base, path_count, it->rays[0], (VCMState*)it->states[0], it->count[0], it->stream), IMBA_ERR_CUDA);
+    g_imba_launches.fetch_add(1);
+    int cur = 0, n = path_count, w = 0;
+    while (n > 0) {
+        const int rc = vcm_wavefront(it, P, algo, true, cur, n);
+        if (rc != IMBA_OK) return rc;
+        cur ^= 1; ++w;
+        IMBA_CUDA(cudaMemcpyAsync(&n, it->count[cur], sizeof(int), cudaMemcpyDeviceToHost, it->stream), IMBA_ERR_CUDA);
+        IMBA_CUDA(cudaStreamSynchronize(it->stream), IMBA_ERR_CUDA);
+        if (w > 4096) { imba_set_error("light pass did not terminate"); return IMBA_ERR_OVERFLOW; }
+    }
+    if (waves) *waves = w;
+    return IMBA_OK;
+}
+
+void imba_vcm_free(imba_integrator* it) {
+    cudaFree(it->cache); cudaFree(it->cache_last); cudaFree(it->grid); cudaFree(it->grid_bbox); cudaFree(it->cells); cudaFree(it->block_sums); cudaFree(it->photons);
+    it->cache = nullptr; it->cache_last = nullptr; it->grid = nullptr; it->grid_bbox = nullptr; it->cells = nullptr; it->block_sums = nullptr; it->photons = nullptr;
+}
+
+int imba_vcm_allocate(imba_integrator* it) {
+    imba_vcm_free(it);
+    const int cap = std::max(it->cache_capacity, 1);
+    it->table = (unsigned)cap * 2u; // inv_load_factor = 2 (rangesearch.h:26)
+    bool ok = cudaMalloc((void**)&it->cache, (size_t)cap * sizeof(DevLightVertex)) == cudaSuccess;
+    ok = ok && cudaMalloc((void**)&it->cache_last, 16) == cudaSuccess && cudaMemset(it->cache_last, 0, 16) == cudaSuccess;
+    ok = ok && cudaMalloc((void**)&it->grid, sizeof(GridParams)) == cudaSuccess && cudaMemset(it->grid, 0, sizeof(GridParams)) == cudaSuccess;
+    ok = ok && cudaMalloc((void**)&it->grid_bbox, 32) == cudaSuccess;
+    ok = ok && cudaMalloc((void**)&it->cells, sizeof(int) * ((size_t)it->table + 1)) == cudaSuccess;
+    ok = ok && cudaMalloc((void**)&it->block_sums, sizeof(int) * ((size_t)it->table / 2048 + 2)) == cudaSuccess;
+    ok = ok && cudaMalloc((void**)&it->photons, (size_t)cap * sizeof(DevPhoton)) == cudaSuccess;
+    if (!ok) { imba_set_error("VCM allocation failed: %s", cudaGetErrorString(cudaGetLastError())); return IMBA_ERR_CUDA; }
+    return IMBA_OK;
+}
+
+/* VCMIntegrator::preprocess (vcm.h:74-81): base radius from the pixel size; LightVertices::compute_cache_size: trace
+ * LIGHT_PATH_LEN_PROBES light paths, count the vertices that would be stored, size the cache to
+ * margin * ceil(average) * path_count with margin 1.1 (10 for tiny path counts), light_vertices.cpp:121-128.
+ * The probe runs the real light pass (with an empty cache, every append is counted and dropped). */
+int imba_vcm_preprocess(imba_integrator* it) {
+    it->base_radius = it->pixel_size * it->cfg.radius_factor;
+    const int algo = it->cfg.algorithm;
+    if (algo == IMBA_ALGO_LT || algo == IMBA_ALGO_VCM_PT) { it->cache_capacity = 0; return imba_vcm_allocate(it); }
+    const int probes = std::min(10000, it->capacity);
+    it->cache_capacity = 0;
+    int rc = imba_vcm_allocate(it);
+    if (rc != IMBA_OK) return rc;
+    VcmParams P = iteration_params(it, 1);
+    float* saved_fb = it->fb; // the probe must not contribute: let its camera connections go to a scratch accumulator
+    float* scratch = nullptr;
+    IMBA_CUDA(cudaMalloc((void**)&scratch, (size_t)it->cfg.width * it->cfg.height * 3 * sizeof(float)), IMBA_ERR_CUDA);
+    it->fb = scratch;
+    unsigned long long stats[2];
+    IMBA_CUDA(cudaMemcpy(stats, it->d_stats, 16, cudaMemcpyDeviceToHost), IMBA_ERR_CUDA);
+    rc = light_pass(it, P, IMBA_ALGO_PPM /* cache appends only */, imba_iteration_seed(it->cfg.seed, ~0ull, 3), probes, nullptr);
+    it->fb = saved_fb; cudaFree(scratch);
+    if (rc != IMBA_OK) return rc;
+    IMBA_CUDA(cudaMemcpy(it->d_stats, stats, 16, cudaMemcpyHostToDevice), IMBA_ERR_CUDA);
+    int vertex_count = 0;
+    IMBA_CUDA(cudaMemcpy(&vertex_count, it->cache_last, sizeof(int), cudaMemcpyDeviceToHost), IMBA_ERR_CUDA);
+    const float avg_len = (float)vertex_count / (float)probes;
+    const float margin = (it->cfg.light_path_count < 10000 / 10) ? 10.0f : 1.1f;
+    const double size = (double)margin * std::ceil(avg_len) * (double)it->cfg.light_path_count;
+    if (size > 1.5e9) { imba_set_error("light vertex cache too large"); return IMBA_ERR_OVERFLOW; }
+    it->cache_capacity = (int)size;
+    return imba_vcm_allocate(it);
+}
+
+int imba_vcm_render_iteration(imba_integrator* it) {
+    if (!it->cache_last) { imba_set_error("imba_integrator_preprocess must be called before rendering with a VCM-family integrator"); return IMBA_ERR_INVALID; }
+    const int algo = it->cfg.algorithm;
+    const uint64_t global_iter = it->iteration * (uint64_t)it->cfg.rank_count + (uint64_t)it->cfg.rank;
+    // the radius schedule follows the GLOBAL iteration index when iterations are sharded over ranks
+    const VcmParams P = iteration_params(it, global_iter + 1);
+    int rc;
+    if (algo != IMBA_ALGO_VCM_PT) {
+        rc = light_pass(it, P, algo, imba_iteration_seed(it->cfg.seed, global_iter, 1), it->cfg.light_path_count, nullptr);
+        if (rc != IMBA_OK) return rc;
+        if (algo != IMBA_ALGO_LT) { // light_vertices_.build(pm_radius_, algo != ALGO_BPT), vcm.cpp:98-99
+            IMBA_CUDA(imba_grid_build(it->cache, it->cache_last, it->cache_capacity, P.pm_radius, it->grid, it->grid_bbox, it->cells, it->table, it->block_sums,
+                                      it->photons, algo != IMBA_ALGO_BPT, it->stream), IMBA_ERR_CUDA);
+            g_imba_launches.fetch_add(algo != IMBA_ALGO_BPT ? 7 : 1);
+        }
+    }
+    if (algo != IMBA_ALGO_LT) {
+        IMBA_CUDA(imba_vcm_camera_raygen(it->cam, P, it->cfg.spp, imba_iteration_seed(it->cfg.seed, global_iter, 2), it->pixel_capacity, it->rays[0],
+                                         (VCMState*)it->states[0], it->count[0], it->stream), IMBA_ERR_CUDA);
+        g_imba_launches.fetch_add(1);
+        int cur = 0;
+        for (int wave = 0; wave < it->cfg.max_path_len; ++wave, cur ^= 1) {
+            rc = vcm_wavefront(it, P, algo, false, cur, it->pixel_capacity);
+            if (rc != IMBA_OK) return rc;
+        }
+    }
+    return IMBA_OK;
+}

@@ -1,0 +1,78 @@
+"""GPU parity of the VCM family (LT, BPT, PPM, VCM and the VCM-style PT) against the reference's own
+VCMIntegrator<algo> (vcm.cpp) running on the oracle: equal-spp renders must agree in mean radiance (< 1.5 %), in
+gamma-0.5 RMSE (the metric of test/run_bench.py:113-129) and in the number of primary / shadow rays per iteration
+(the reference's TileScheduler counters, tile_scheduler.h:117-127), and the unbiased algorithms must agree with each
+other.  Hash-grid build/query and the light-vertex cache are exercised by PPM / VCM (merging) and BPT / VCM (connections)."""
+import os
+
+import numpy as np
+import pytest
+
+from tests import refapi
+from tests.conftest import load_scene
+
+pytestmark = pytest.mark.gpu
+needs_ref = pytest.mark.skipif(not refapi.have_ref() or not os.path.isdir(refapi.REF_SCENES), reason="oracle/_ref not built")
+REF_ALGO = {"pt": 0, "bpt": 1, "vcm": 2, "ppm": 3, "vcm_pt": 4, "lt": 5}  # UserSettings::Algorithm, frontend/cmd_line.h:41-48
+
+
+def gamma_rmse(a, b):
+    return float(np.sqrt(np.mean((np.clip(a, 0, 1) ** 0.5 - np.clip(b, 0, 1) ** 0.5) ** 2)))
+
+
+@pytest.fixture(scope="module")
+def rendered():
+    from imbatracer_b200 import api
+    flat = load_scene("cornell_org", "gpu")
+    sc = api.Scene(flat)
+    out = {}
+    n = 48
+    for algo in ("pt", "vcm_pt", "lt", "bpt", "ppm", "vcm"):
+        it = api.Integrator(sc, api.render_settings(flat, algo, 96, 96, seed=11))
+        it.preprocess()
+        it.render(n)
+        img = it.download() / n
+        out[algo] = (img, tuple(c / n for c in it.ray_counts()))
+        it.close()
+    sc.close()
+    return out
+
+
+def test_algorithms_agree_with_each_other(rendered):
+    pt = rendered["pt"][0]
+    for algo in ("bpt", "ppm", "vcm"):
+        img = rendered[algo][0]
+        assert np.isfinite(img).all() and img.min() >= 0
+        assert abs(img.mean() - pt.mean()) < 0.02 * pt.mean(), algo
+        assert gamma_rmse(img, pt) < 0.04, algo
+    # light tracing only sees paths that end at the camera through a connection: darker, never brighter than PT
+    lt = rendered["lt"][0]
+    assert 0.2 * pt.mean() < lt.mean() < pt.mean()
+
+
+@needs_ref
+@pytest.mark.parametrize("algo,tol", [("vcm_pt", 0.04), ("lt", 0.06), ("bpt", 0.03), ("ppm", 0.035), ("vcm", 0.035)])
+def test_matches_reference_integrator(rendered, algo, tol):
+    img, (prim, shad) = rendered[algo]
+    rs = refapi.RefScene(os.path.join(refapi.REF_SCENES, "cornell", "cornell_org.scene"), True)
+    n = 32
+    ref, st = rs.render(REF_ALGO[algo], 96, 96, iterations=n)
+    rs.close()
+    ref = ref / n
+    assert abs(img.mean() - ref.mean()) < 0.015 * ref.mean(), (img.mean(), ref.mean())
+    assert gamma_rmse(img, ref) < tol
+    assert abs(prim - st["primary_rays"] / n) < 0.02 * prim
+    assert abs(shad - st["shadow_rays"] / n) <= 0.02 * max(shad, 1)
+
+
+def test_vcm_needs_preprocess_and_valid_settings():
+    from imbatracer_b200 import abi, api
+    flat = load_scene("cornell_org", "gpu")
+    sc = api.Scene(flat)
+    it = api.Integrator(sc, api.render_settings(flat, "vcm", 32, 32))
+    with pytest.raises(RuntimeError, match="preprocess"):
+        it.render(1)
+    it.close()
+    with pytest.raises(RuntimeError, match="knn"):
+        api.Integrator(sc, api.render_settings(flat, "vcm", 32, 32, num_knn=64))
+    sc.close()
