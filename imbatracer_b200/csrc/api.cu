@@ -2,6 +2,7 @@
  * Signatures: include/imba_b200.h.  There is no CPU fallback anywhere in this library: without a CUDA
  * device every entry point fails (L2: negative status + imba_last_error(); L1: message + abort()). */
 #include "api_common.h"
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -37,7 +38,8 @@ int imba_scene_upload_accel(imba_scene* s, const Bvh8& b) {
     if ((rc = upload(&s->d_tris, b.tris.data(), b.tris.size() * sizeof(Tri48)))) return rc;
     if ((rc = upload(&s->d_insts, b.insts.data(), b.insts.size() * sizeof(Inst64)))) return rc;
     if ((rc = upload(&s->d_counters, nullptr, imba_scene::kCounters * sizeof(unsigned)))) return rc;
-    s->top_root = b.top_root;
+    s->top_root = b.flat ? b.flat_root : b.top_root; s->flat_inst = b.flat && !getenv("IMBA_NO_FLAT") ? b.flat_inst : -1;
+    if (s->flat_inst < 0) s->top_root = b.top_root;
     s->stats[0] = (int64_t)b.nodes.size(); s->stats[1] = (int64_t)b.tris.size() - 1; s->stats[2] = (int64_t)b.insts.size();
     s->stats[3] = (int64_t)(b.nodes.size() * sizeof(Node8) + b.tris.size() * sizeof(Tri48) + b.insts.size() * sizeof(Inst64));
     s->stats[4] = b.max_depth;
@@ -113,7 +115,7 @@ int imba_scene_trace_ex(imba_scene* s, const TraceRequest& rq, cudaStream_t stre
     unsigned* ctr = s->d_counters + (s->next_counter.fetch_add(1) % imba_scene::kCounters);
     IMBA_CUDA(cudaMemsetAsync(ctr, 0, sizeof(unsigned), stream), IMBA_ERR_CUDA);
     TraceArgs a;
-    a.nodes = s->d_nodes; a.tris = s->d_tris; a.insts = s->d_insts; a.top_root = s->top_root;
+    a.nodes = s->d_nodes; a.tris = s->d_tris; a.insts = s->d_insts; a.top_root = s->top_root; a.flat_inst = s->flat_inst;
     a.rays = (const float4*)rq.d_rays; a.hits = (int4*)rq.d_hits; a.count = rq.capacity; a.count_ptr = rq.d_count; a.count_mul = rq.count_mul; a.counter = ctr; a.stats = rq.d_counters;
     a.indices = s->d_mask_indices; a.texcoords = s->d_mask_texcoords; a.masks = s->d_masks; a.mask_buffer = s->d_mask_buffer;
     a.shadow_states = rq.d_shadow_states; a.framebuffer = rq.d_framebuffer;

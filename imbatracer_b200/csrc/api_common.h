@@ -26,7 +26,7 @@ struct imba_scene {
     int       sm_count = 0;
     // acceleration structure
     uint4*    d_nodes = nullptr; float4* d_tris = nullptr; float4* d_insts = nullptr;
-    uint32_t  top_root = 0;
+    uint32_t  top_root = 0; int flat_inst = -1;
     int64_t   stats[5] = { 0, 0, 0, 0, 0 };
     // opacity masks
     bool      has_masks = false; bool owns_masks = true;

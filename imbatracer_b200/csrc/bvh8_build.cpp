@@ -365,6 +365,10 @@ bool imba_build_bvh8(int layout, int root, const void* nodes, const imba_vec4* t
     out.top_root = em.run();
     out.max_depth = em.max_depth + mesh_depth;
     out.ref_node_count = visited;
+    if (out.insts.size() == 1) {
+        static const float ident[12] = { 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0 };
+        if (memcmp(out.insts[0].m, ident, sizeof(ident)) == 0) { out.flat = true; out.flat_root = (uint32_t)out.insts[0].root; out.flat_inst = out.insts[0].inst_id; }
+    }
     // one padding triangle so that 3-wide speculative loads past the last leaf stay in bounds
     Tri48 pad; memset(&pad, 0, sizeof(pad)); pad.id = (int32_t)0x80000000; out.tris.push_back(pad);
     return true;

@@ -13,6 +13,9 @@ struct Bvh8 {
     uint32_t top_root = 0;   // Node8 index of the top-level root
     int      max_depth = 0;  // deepest root-to-leaf path (top level + mesh level)
     int      ref_node_count = 0; // nodes of the reference structure that were visited
+    // single instance with the identity transform (every scene of the reference's test set except cornell_instances):
+    // traversal may start in the mesh tree directly, the result is bit-identical (1*x + 0 is exact)
+    bool     flat = false; uint32_t flat_root = 0; int32_t flat_inst = 0;
 };
 
 /* layout: IMBA_ACCEL_MBVH4 (nodes = imba_node4[]) or IMBA_ACCEL_BVH2 (nodes = imba_node2[]); all pointers are host

@@ -11,6 +11,7 @@ struct TraceArgs {
     const float4*  tris;       // Tri48[] as 3 x float4
     const float4*  insts;      // Inst64[] as 4 x float4
     uint32_t       top_root;
+    int            flat_inst;  // >= 0: single identity instance, top_root is the mesh root and rays never change space
     const float4*  rays;       // imba_ray[] as 2 x float4
     int4*          hits;       // imba_hit[]
     int            count;

@@ -106,8 +106,12 @@ __global__ void __launch_bounds__(BLOCK_THREADS) trace_kernel(const TraceArgs P)
                 if (take) {
                     ray_idx = (int)i;
                     const float4 o = __ldcs(P.rays + 2 * i), d = __ldcs(P.rays + 2 * i + 1);
-                    r.ox = o.x; r.oy = o.y; r.oz = o.z; r.dx = d.x; r.dy = d.y; r.dz = d.z; r.finish();
-                    tmin = o.w; tbest = d.w; ubest = 0.0f; tri_best = IMBA_NO_HIT; inst_best = IMBA_NO_HIT; cur_inst = -1;
+                    r.ox = o.x; r.oy = o.y; r.oz = o.z; r.dx = d.x; r.dy = d.y; r.dz = d.z;
+                    if (P.flat_inst >= 0) { // the identity transform of the skipped instance turns -0 into +0 (1 * x + 0)
+                        r.ox += 0.0f; r.oy += 0.0f; r.oz += 0.0f; r.dx += 0.0f; r.dy += 0.0f; r.dz += 0.0f;
+                    }
+                    r.finish();
+                    tmin = o.w; tbest = d.w; ubest = 0.0f; tri_best = IMBA_NO_HIT; inst_best = IMBA_NO_HIT; cur_inst = P.flat_inst;
                     sp = 0; ngroup = make_uint2(P.top_root, 0x80000000u); tgroup = make_uint2(0, 0);
                     if (STATS) { st_nodes = st_tris = st_insts = st_sp = 0; }
                     active = true;
