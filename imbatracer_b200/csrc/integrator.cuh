@@ -84,7 +84,18 @@ uint32_t imba_iteration_seed(uint64_t seed, uint64_t global_iteration, uint32_t 
 
 cudaError_t imba_pt_raygen(const DevCamera& cam, int spp, uint32_t seed_base, int first, int count, float4* rays, PTState* states, int* count_out, cudaStream_t st);
 cudaError_t imba_pt_shade(const DeviceShading& S, float4* rays, const int4* hits, PTState* states, const int* sorted, const int* hit_count_ptr, const int* queue_count_ptr, int capacity,
-                          float4* shadow_rays, ShadowState* shadow_states, float* fb, int max_path_len, unsigned long long* ray_stats, cudaStream_t st);
+                          float4* shadow_rays, ShadowState* shadow_states, float* fb, int max_path_len, unsigned long long* ray_stats,
+                          float4* out_rays, PTState* out_states, int* out_count, cudaStream_t st);
+
+/* Warp-aggregated queue push (RayQueue::push, ray_queue.h:123-130): one atomicAdd per converged group of lanes. */
+__device__ __forceinline__ int queue_push_slot(int* count) {
+    const unsigned m = __activemask();
+    const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(count, __popc(m));
+    base = __shfl_sync(m, base, leader);
+    return base + __popc(m & ((1u << lane) - 1u));
+}
 cudaError_t imba_probe_raygen(const DevCamera& cam, float4* rays, int count, cudaStream_t st);
 cudaError_t imba_probe_reduce(const float4* rays, const int4* hits, int quads, float* total, int* count, cudaStream_t st);
 cudaError_t imba_clear_shadow(ShadowState* s, int n, cudaStream_t st);

@@ -36,7 +36,8 @@ __global__ void pt_raygen_kernel(DevCamera cam, int spp, uint32_t seed_base, int
 
 __global__ void __launch_bounds__(128) pt_shade_kernel(const DeviceShading S, float4* rays, const int4* hits, PTState* states, const int* sorted,
                                                        const int* hit_count_ptr, const int* queue_count_ptr, float4* shadow_rays, ShadowState* shadow_states,
-                                                       float* fb, int max_path_len, unsigned long long* ray_stats) {
+                                                       float* fb, int max_path_len, unsigned long long* ray_stats, float4* out_rays, PTState* out_states,
+                                                       int* out_count) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int hit_count = *hit_count_ptr;
     if (i == 0 && ray_stats) atomicAdd(ray_stats, (unsigned long long)*queue_count_ptr); // rays traced in this wavefront (tile_scheduler.h:117-127)
@@ -108,9 +109,12 @@ __global__ void __launch_bounds__(128) pt_shade_kernel(const DeviceShading S, fl
             st.tr = thr.x; st.tg = thr.y; st.tb = thr.z;
             st.bounces_spec = (uint32_t)(bounces + 1) | ((flags & BSDF_SPECULAR) ? 0x80000000u : 0u);
             st.last_pdf = pdf; st.rng = rng.s;
-            states[idx] = st;
-            rays[2 * idx] = make_float4(is.pos.x, is.pos.y, is.pos.z, offset);
-            rays[2 * idx + 1] = make_float4(dir.x, dir.y, dir.z, FLT_MAX);
+            // continuation: in place like the reference (then compact_rays), or straight into the next wavefront's queue
+            const int o = out_count ? queue_push_slot(out_count) : idx;
+            (out_count ? out_states : states)[o] = st;
+            float4* dst = (out_count ? out_rays : rays) + 2 * (size_t)o;
+            dst[0] = make_float4(is.pos.x, is.pos.y, is.pos.z, offset);
+            dst[1] = make_float4(dir.x, dir.y, dir.z, FLT_MAX);
         }
     }
     if (!alive) states[idx].pixel_id = -1;
@@ -154,9 +158,10 @@ cudaError_t imba_pt_raygen(const DevCamera& cam, int spp, uint32_t seed_base, in
 }
 
 cudaError_t imba_pt_shade(const DeviceShading& S, float4* rays, const int4* hits, PTState* states, const int* sorted, const int* hit_count_ptr, const int* queue_count_ptr, int capacity,
-                          float4* shadow_rays, ShadowState* shadow_states, float* fb, int max_path_len, unsigned long long* ray_stats, cudaStream_t st) {
+                          float4* shadow_rays, ShadowState* shadow_states, float* fb, int max_path_len, unsigned long long* ray_stats, float4* out_rays, PTState* out_states,
+                          int* out_count, cudaStream_t st) {
     if (capacity <= 0) return cudaSuccess;
-    pt_shade_kernel<<<(capacity + 127) / 128, 128, 0, st>>>(S, rays, hits, states, sorted, hit_count_ptr, queue_count_ptr, shadow_rays, shadow_states, fb, max_path_len, ray_stats);
+    pt_shade_kernel<<<(capacity + 127) / 128, 128, 0, st>>>(S, rays, hits, states, sorted, hit_count_ptr, queue_count_ptr, shadow_rays, shadow_states, fb, max_path_len, ray_stats, out_rays, out_states, out_count);
     return cudaGetLastError();
 }
 

@@ -123,6 +123,31 @@ __global__ void __launch_bounds__(PART_THREADS) part_scatter(const int* keys, co
     }
 }
 
+/* Same scatter without the per-warp turn taking: positions inside a (block, bin) range are handed out by shared-memory
+ * atomics (one per distinct key per warp).  Grouping is identical, the order inside a group depends on warp timing --
+ * what the reference's own scatter does (ray_queue.h:235-243); used by the integrators, where only the grouping matters. */
+__global__ void __launch_bounds__(PART_THREADS) part_scatter_fast(const int* keys, const int* count_ptr, int count_imm, int nbins, const int* block_off, int* out_idx) {
+    extern __shared__ int bin_base[];
+    const int n = count_ptr ? *count_ptr : count_imm;
+    const int base = blockIdx.x * PART_CHUNK;
+    if (base >= n) return;
+    for (int b = threadIdx.x; b < nbins; b += PART_THREADS) bin_base[b] = block_off[b * gridDim.x + blockIdx.x];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    for (int k = threadIdx.x; k < PART_CHUNK; k += PART_THREADS) {
+        const int i = base + k;
+        if (i < n) {
+            const int kk = keys[i];
+            const unsigned peers = __match_any_sync(__activemask(), kk);
+            const int leader = __ffs(peers) - 1;
+            int pos = 0;
+            if (lane == leader) pos = atomicAdd(&bin_base[kk], __popc(peers));
+            pos = __shfl_sync(peers, pos, leader);
+            out_idx[pos + __popc(peers & ((1u << lane) - 1u))] = i;
+        }
+    }
+}
+
 /* compact_rays: out[j] = in[idx[j]] for j < *kept; 16-byte vector copies of the 32-byte ray, 8-byte copies of the state */
 __global__ void gather_rays_states(const float4* rays, const char* states, int state_bytes, const int* idx, const int* kept_ptr,
                                    float4* rays_out, char* states_out, int* count_out) {
@@ -151,13 +176,14 @@ __global__ void gather_queue(const float4* rays, const int4* hits, const char* s
 }
 
 template <class KeyFn>
-cudaError_t run_partition(const PartitionBuffers& b, KeyFn key, const int* count_ptr, int count_imm, int capacity, int nbins, cudaStream_t st) {
+cudaError_t run_partition(const PartitionBuffers& b, KeyFn key, const int* count_ptr, int count_imm, int capacity, int nbins, cudaStream_t st, bool stable = true) {
     if (capacity <= 0) return cudaSuccess;
     const int nblocks = (capacity + PART_CHUNK - 1) / PART_CHUNK;
     if (nblocks > b.max_blocks || nbins > b.max_bins) return cudaErrorInvalidValue;
     part_hist<KeyFn><<<nblocks, PART_THREADS, nbins * sizeof(int), st>>>(key, count_ptr, count_imm, nbins, b.keys, b.block_hist);
     part_scan<<<1, 1024, 0, st>>>(nblocks, nbins, b.block_hist, b.bin_start);
-    part_scatter<<<nblocks, PART_THREADS, nbins * sizeof(int), st>>>(b.keys, count_ptr, count_imm, nbins, b.block_hist, b.indices);
+    if (stable) part_scatter<<<nblocks, PART_THREADS, nbins * sizeof(int), st>>>(b.keys, count_ptr, count_imm, nbins, b.block_hist, b.indices);
+    else        part_scatter_fast<<<nblocks, PART_THREADS, nbins * sizeof(int), st>>>(b.keys, count_ptr, count_imm, nbins, b.block_hist, b.indices);
     return cudaGetLastError();
 }
 
@@ -179,8 +205,8 @@ void imba_partition_free(PartitionBuffers& b) {
 }
 
 cudaError_t imba_sort_hits_by_material(const PartitionBuffers& b, const int4* hits, const int4* indices, int nmat, int* shadow_pixel, int shadow_slots,
-                                       const int* count_ptr, int count_imm, int capacity, cudaStream_t st) {
-    return run_partition(b, HitMaterialKey{ hits, indices, nmat, shadow_pixel, shadow_slots }, count_ptr, count_imm, capacity, nmat + 1, st);
+                                       const int* count_ptr, int count_imm, int capacity, cudaStream_t st, bool stable) {
+    return run_partition(b, HitMaterialKey{ hits, indices, nmat, shadow_pixel, shadow_slots }, count_ptr, count_imm, capacity, nmat + 1, st, stable);
 }
 
 cudaError_t imba_compact_alive(const PartitionBuffers& b, const int4* hits, const float4* rays, const void* states, int state_bytes,

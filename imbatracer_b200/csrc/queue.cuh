@@ -6,7 +6,7 @@
 #include <stdint.h>
 
 constexpr int PART_THREADS = 256;
-constexpr int PART_CHUNK = 2048;   // elements per block
+constexpr int PART_CHUNK = 8192;   // elements per block
 
 struct PartitionBuffers {
     int* keys = nullptr;        // [capacity]
@@ -22,7 +22,7 @@ void        imba_partition_free(PartitionBuffers& b);
 /* compact_hits + sort_by_material: b.indices[0 .. b.bin_start[nmat]) = hit rays grouped by material (stable);
  * b.bin_start[nmat] = hit count.  shadow_pixel (optional): ShadowState array (shadow_slots per ray) whose pixel_id is reset to -1. */
 cudaError_t imba_sort_hits_by_material(const PartitionBuffers& b, const int4* hits, const int4* indices, int nmat, int* shadow_pixel, int shadow_slots,
-                                       const int* count_ptr, int count_imm, int capacity, cudaStream_t st);
+                                       const int* count_ptr, int count_imm, int capacity, cudaStream_t st, bool stable = true);
 /* compact_rays: stable copy of the live rays + states (hits == nullptr: pixel_id >= 0; else also hit.tri_id >= 0). */
 cudaError_t imba_compact_alive(const PartitionBuffers& b, const int4* hits, const float4* rays, const void* states, int state_bytes,
                                const int* count_ptr, int count_imm, int capacity, float4* rays_out, void* states_out, int* count_out, cudaStream_t st);

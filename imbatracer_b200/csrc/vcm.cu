@@ -89,7 +89,7 @@ template <int ALGO>
 __global__ void __launch_bounds__(128) vcm_light_shade_kernel(const DeviceShading S, const VcmParams P, const DevCamera cam, float4* rays, const int4* hits, VCMState* states,
                                                               const int* sorted, const int* hit_count_ptr, const int* queue_count_ptr, float4* shadow_rays,
                                                               ShadowState* shadow_states, DevLightVertex* cache, int cache_capacity, int* cache_last,
-                                                              unsigned long long* ray_stats) {
+                                                              unsigned long long* ray_stats, float4* out_rays, VCMState* out_states, int* out_count) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i == 0 && ray_stats) atomicAdd(ray_stats, (unsigned long long)*queue_count_ptr);
     if (i >= *hit_count_ptr) return;
@@ -157,7 +157,10 @@ __global__ void __launch_bounds__(128) vcm_light_shade_kernel(const DeviceShadin
     float4 no, nd;
     if (vcm_bounce<ALGO>(P, st, rng, is, bsdf, true, t * 1e-4f, no, nd)) {
         st.rng = rng.s;
-        states[idx] = st; rays[2 * idx] = no; rays[2 * idx + 1] = nd;
+        const int o = out_count ? queue_push_slot(out_count) : idx;
+        (out_count ? out_states : states)[o] = st;
+        float4* dst = (out_count ? out_rays : rays) + 2 * (size_t)o;
+        dst[0] = no; dst[1] = nd;
     } else states[idx].pixel_id = -1;
 }
 
@@ -323,7 +326,8 @@ template <int ALGO>
 __global__ void __launch_bounds__(128) vcm_camera_shade_kernel(const DeviceShading S, const VcmParams P, float4* rays, const int4* hits, VCMState* states, const int* sorted,
                                                                const int* hit_count_ptr, const int* queue_count_ptr, float4* shadow_rays, ShadowState* shadow_states,
                                                                const DevLightVertex* cache, const GridParams* gp, const int* cells, unsigned table,
-                                                               const DevPhoton* photons, float* fb, unsigned long long* ray_stats) {
+                                                               const DevPhoton* photons, float* fb, unsigned long long* ray_stats, float4* out_rays, VCMState* out_states,
+                                                               int* out_count) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i == 0 && ray_stats) atomicAdd(ray_stats, (unsigned long long)*queue_count_ptr);
     if (i >= *hit_count_ptr) return;
@@ -438,20 +442,23 @@ __global__ void __launch_bounds__(128) vcm_camera_shade_kernel(const DeviceShadi
     float4 no, nd;
     if (vcm_bounce<ALGO>(P, st, rng, is, bsdf, false, t * 1e-4f, no, nd)) {
         st.rng = rng.s;
-        states[idx] = st; rays[2 * idx] = no; rays[2 * idx + 1] = nd;
+        const int o = out_count ? queue_push_slot(out_count) : idx;
+        (out_count ? out_states : states)[o] = st;
+        float4* dst = (out_count ? out_rays : rays) + 2 * (size_t)o;
+        dst[0] = no; dst[1] = nd;
     } else states[idx].pixel_id = -1;
 }
 
 template <int ALGO>
 cudaError_t light_shade(const VcmLaunch& a, cudaStream_t st) {
     vcm_light_shade_kernel<ALGO><<<(a.capacity + 127) / 128, 128, 0, st>>>(*a.S, a.P, a.cam, a.rays, a.hits, a.states, a.sorted, a.hit_count_ptr, a.queue_count_ptr,
-                                                                          a.shadow_rays, a.shadow_states, a.cache, a.cache_capacity, a.cache_last, a.ray_stats);
+                                                                          a.shadow_rays, a.shadow_states, a.cache, a.cache_capacity, a.cache_last, a.ray_stats, a.out_rays, a.out_states, a.out_count);
     return cudaGetLastError();
 }
 template <int ALGO>
 cudaError_t camera_shade(const VcmLaunch& a, cudaStream_t st) {
     vcm_camera_shade_kernel<ALGO><<<(a.capacity + 127) / 128, 128, 0, st>>>(*a.S, a.P, a.rays, a.hits, a.states, a.sorted, a.hit_count_ptr, a.queue_count_ptr, a.shadow_rays,
-                                                                           a.shadow_states, a.cache, a.grid, a.cells, a.table, a.photons, a.fb, a.ray_stats);
+                                                                           a.shadow_states, a.cache, a.grid, a.cells, a.table, a.photons, a.fb, a.ray_stats, a.out_rays, a.out_states, a.out_count);
     return cudaGetLastError();
 }
 

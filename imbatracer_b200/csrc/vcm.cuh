@@ -21,6 +21,7 @@ struct VcmLaunch {
     DevLightVertex* cache; int cache_capacity; int* cache_last;
     const GridParams* grid; const int* cells; unsigned table; const DevPhoton* photons;
     float* fb; unsigned long long* ray_stats;
+    float4* out_rays; VCMState* out_states; int* out_count; // next wavefront's queue (fused compaction)
 };
 
 cudaError_t imba_vcm_light_raygen(const DeviceShading& S, const VcmParams& P, uint32_t seed_base, int count, float4* rays, VCMState* states, int* count_out, cudaStream_t st);

@@ -33,6 +33,7 @@ static VcmLaunch base_launch(imba_integrator* it, const VcmParams& P, int cur, i
     a.cache = it->cache; a.cache_capacity = it->cache_capacity; a.cache_last = it->cache_last;
     a.grid = it->grid; a.cells = it->cells; a.table = it->table; a.photons = it->photons;
     a.fb = it->fb; a.ray_stats = it->d_stats;
+    a.out_rays = it->rays[cur ^ 1]; a.out_states = (VCMState*)it->states[cur ^ 1]; a.out_count = it->count[cur ^ 1];
     return a;
 }
 
@@ -43,7 +44,8 @@ static int vcm_wavefront(imba_integrator* it, const VcmParams& P, int algo, bool
     TraceRequest rq; rq.d_rays = (const imba_ray*)it->rays[cur]; rq.d_hits = (imba_hit*)it->hits; rq.capacity = capacity; rq.d_count = it->count[cur]; rq.mode = 0;
     int rc = imba_scene_trace_ex(it->scene, rq, it->stream);
     if (rc != IMBA_OK) return rc;
-    IMBA_CUDA(imba_sort_hits_by_material(it->part, it->hits, S.indices, S.material_count, (int*)it->shadow_states, slots, it->count[cur], 0, capacity, it->stream), IMBA_ERR_CUDA);
+    IMBA_CUDA(imba_sort_hits_by_material(it->part, it->hits, S.indices, S.material_count, (int*)it->shadow_states, slots, it->count[cur], 0, capacity, it->stream, false), IMBA_ERR_CUDA);
+    IMBA_CUDA(cudaMemsetAsync(it->count[cur ^ 1], 0, sizeof(int), it->stream), IMBA_ERR_CUDA);
     const VcmLaunch a = base_launch(it, P, cur, capacity);
     IMBA_CUDA(light ? imba_vcm_light_shade(algo, a, it->stream) : imba_vcm_camera_shade(algo, a, it->stream), IMBA_ERR_CUDA);
     const bool shadows = light ? algo != IMBA_ALGO_PPM : algo != IMBA_ALGO_PPM; // PPM emits no shadow rays in either pass
@@ -53,9 +55,8 @@ static int vcm_wavefront(imba_integrator* it, const VcmParams& P, int algo, bool
         rc = imba_scene_trace_ex(it->scene, sq, it->stream);
         if (rc != IMBA_OK) return rc;
     }
-    IMBA_CUDA(imba_compact_alive(it->part, it->hits, it->rays[cur], it->states[cur], it->state_bytes, it->count[cur], 0, capacity,
-                                 it->rays[cur ^ 1], it->states[cur ^ 1], it->count[cur ^ 1], it->stream), IMBA_ERR_CUDA);
-    g_imba_launches.fetch_add(3 + 1 + 4 + (shadows ? 1 : 0));
+    // survivors were pushed into the other queue by the shading kernel (fused, unordered compaction)
+    g_imba_launches.fetch_add(3 + 1 + 1 + (shadows ? 1 : 0));
     return IMBA_OK;
 }
 

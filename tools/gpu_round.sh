@@ -13,6 +13,6 @@ if [ "$1" = "ncu" ]; then
 python bench.py --steps 2 --warmup 3 > gpurun_out/plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 > gpurun_out/ncu_list.log 2>&1
 python bench.py --steps 2 --warmup 3 > gpurun_out/plain2.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:trace_kernel -s 20 -c 4 -o gpurun_out/prof python bench.py --steps 2 --warmup 3 > gpurun_out/ncu_full.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:trace_kernel -s 24 -c 4 -o gpurun_out/prof python bench.py --steps 2 --warmup 3 > gpurun_out/ncu_full.log 2>&1
 tail -3 gpurun_out/ncu_full.log
 fi
