@@ -85,7 +85,7 @@ extern "C" void imba_scene_destroy(imba_scene* s) {
     if (!s) return;
     cudaFree(s->d_nodes); cudaFree(s->d_tris); cudaFree(s->d_insts); cudaFree(s->d_counters);
     if (s->owns_masks) { cudaFree(s->d_mask_indices); cudaFree(s->d_mask_texcoords); cudaFree(s->d_masks); cudaFree(s->d_mask_buffer); }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < imba_scene::kStageSlots; ++i) {
         cudaFree(s->d_stage_rays[i]); cudaFree(s->d_stage_hits[i]);
         if (s->stage_stream[i]) cudaStreamDestroy(s->stage_stream[i]);
     }
@@ -112,7 +112,7 @@ int imba_scene_trace_ex(imba_scene* s, const TraceRequest& rq, cudaStream_t stre
     const int warps_per_block = imba_trace_block_threads() / 32;
     const int needed = (rq.capacity + 32 * warps_per_block - 1) / (32 * warps_per_block);
     const int grid = needed < s->grid_cache[variant] ? needed : s->grid_cache[variant];
-    unsigned* ctr = s->d_counters + (s->next_counter.fetch_add(1) % imba_scene::kCounters);
+    unsigned* ctr = rq.d_work_counter ? rq.d_work_counter : s->d_counters + (s->next_counter.fetch_add(1) % imba_scene::kCounters);
     IMBA_CUDA(cudaMemsetAsync(ctr, 0, sizeof(unsigned), stream), IMBA_ERR_CUDA);
     TraceArgs a;
     a.nodes = s->d_nodes; a.tris = s->d_tris; a.insts = s->d_insts; a.top_root = s->top_root; a.flat_inst = s->flat_inst;
@@ -139,20 +139,20 @@ extern "C" int imba_trace(imba_scene* s, const imba_ray* d_rays, imba_hit* d_hit
 static std::mutex g_stage_mutex;
 
 /* RayQueue::traverse_gpu / traverse_occluded_gpu (ray_queue.h:269-293, 319-343) with the copies overlapped:
- * chunk k+1 is uploaded on the other stream while chunk k is traced and its hits are downloaded. */
+ * chunks rotate over kStageSlots streams, so uploads, traversal and downloads of different chunks overlap (both copy engines busy). */
 extern "C" int imba_trace_host(imba_scene* s, const imba_ray* h_rays, imba_hit* h_hits, int count, int any_hit) {
     if (!s || count < 0 || (count > 0 && (!h_rays || !h_hits))) { imba_set_error("invalid traversal arguments"); return IMBA_ERR_INVALID; }
     if (count == 0) return IMBA_OK;
     std::lock_guard<std::mutex> lock(g_stage_mutex);
     const int chunk = imba_scene::kChunkRays;
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < imba_scene::kStageSlots; ++i) {
         if (s->d_stage_rays[i]) continue;
         IMBA_CUDA(cudaMalloc((void**)&s->d_stage_rays[i], (size_t)chunk * sizeof(imba_ray)), IMBA_ERR_CUDA);
         IMBA_CUDA(cudaMalloc((void**)&s->d_stage_hits[i], (size_t)chunk * sizeof(imba_hit)), IMBA_ERR_CUDA);
         IMBA_CUDA(cudaStreamCreateWithFlags(&s->stage_stream[i], cudaStreamNonBlocking), IMBA_ERR_CUDA);
     }
     int k = 0;
-    for (int first = 0; first < count; first += chunk, k ^= 1) {
+    for (int first = 0; first < count; first += chunk, k = (k + 1) % imba_scene::kStageSlots) {
         const int n = count - first < chunk ? count - first : chunk;
         cudaStream_t st = s->stage_stream[k];
         IMBA_CUDA(cudaMemcpyAsync(s->d_stage_rays[k], h_rays + first, (size_t)n * sizeof(imba_ray), cudaMemcpyHostToDevice, st), IMBA_ERR_CUDA);
@@ -160,8 +160,7 @@ extern "C" int imba_trace_host(imba_scene* s, const imba_ray* h_rays, imba_hit* 
         if (rc != IMBA_OK) return rc;
         IMBA_CUDA(cudaMemcpyAsync(h_hits + first, s->d_stage_hits[k], (size_t)n * sizeof(imba_hit), cudaMemcpyDeviceToHost, st), IMBA_ERR_CUDA);
     }
-    IMBA_CUDA(cudaStreamSynchronize(s->stage_stream[0]), IMBA_ERR_CUDA);
-    IMBA_CUDA(cudaStreamSynchronize(s->stage_stream[1]), IMBA_ERR_CUDA);
+    for (int i = 0; i < imba_scene::kStageSlots; ++i) IMBA_CUDA(cudaStreamSynchronize(s->stage_stream[i]), IMBA_ERR_CUDA);
     return IMBA_OK;
 }
 

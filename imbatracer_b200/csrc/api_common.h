@@ -35,9 +35,10 @@ struct imba_scene {
     unsigned* d_counters = nullptr; std::atomic<unsigned> next_counter{ 0 };
     static constexpr unsigned kCounters = 4096;
     // staging for host-buffer traversal
-    static constexpr int kChunkRays = 1 << 20;
-    float4*   d_stage_rays[2] = { nullptr, nullptr }; int4* d_stage_hits[2] = { nullptr, nullptr };
-    cudaStream_t stage_stream[2] = { nullptr, nullptr };
+    static constexpr int kChunkRays = 1 << 19;   // 16 MiB of rays up, 8 MiB of hits down per chunk
+    static constexpr int kStageSlots = 4;        // chunks in flight: H2D, traversal and D2H of different chunks overlap
+    float4*   d_stage_rays[kStageSlots] = {}; int4* d_stage_hits[kStageSlots] = {};
+    cudaStream_t stage_stream[kStageSlots] = {};
     // shading data (geometry, materials, lights, textures), null until uploaded
     DeviceShading* shading = nullptr;
     int grid_cache[12] = { 0 };
@@ -53,6 +54,7 @@ struct TraceRequest {
     int count_mul = 1;              // ray count = *d_count * count_mul
     int mode = 0;                   // 0 closest, 1 any hit, 2 any hit + shadow resolve
     uint32_t* d_counters = nullptr;
+    unsigned* d_work_counter = nullptr; // optional dedicated work counter (launches captured into a CUDA graph)
     const void* d_shadow_states = nullptr; float* d_framebuffer = nullptr;
 };
 int imba_scene_trace_ex(imba_scene* s, const TraceRequest& rq, cudaStream_t stream);

@@ -72,6 +72,9 @@ struct imba_integrator {
     struct GridParams* grid = nullptr; int* grid_bbox = nullptr; int* cells = nullptr; unsigned table = 0; int* block_sums = nullptr;
     struct DevPhoton* photons = nullptr;
     float   base_radius = 0.0f;
+    struct VcmParams* d_params = nullptr;    // per-iteration constants in device memory
+    unsigned* tail_counters = nullptr; int tail_counter_next = -1; // dedicated traversal work counters of the captured graph
+    cudaGraphExec_t tail_graph = nullptr;    // captured light-pass wavefronts for the long tail of small queues
 };
 int imba_vcm_allocate(imba_integrator* it);
 void imba_vcm_free(imba_integrator* it);

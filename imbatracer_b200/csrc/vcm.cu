@@ -30,7 +30,8 @@ __device__ __forceinline__ Bsdf vertex_bsdf(const DeviceShading& S, const DevLig
 }
 
 /* ---- light pass ------------------------------------------------------------------------------------------- */
-__global__ void vcm_light_raygen_kernel(const DeviceShading S, VcmParams P, uint32_t seed_base, int count, float4* rays, VCMState* states, int* count_out) {
+__global__ void vcm_light_raygen_kernel(const DeviceShading S, const VcmParams* Pd, uint32_t seed_base, int count, float4* rays, VCMState* states, int* count_out) {
+    const VcmParams P = *Pd;
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p == 0) *count_out = count;
     if (p >= count) return;
@@ -86,10 +87,11 @@ __device__ __forceinline__ bool vcm_bounce(const VcmParams& P, VCMState& st, Rng
 }
 
 template <int ALGO>
-__global__ void __launch_bounds__(128) vcm_light_shade_kernel(const DeviceShading S, const VcmParams P, const DevCamera cam, float4* rays, const int4* hits, VCMState* states,
+__global__ void __launch_bounds__(128) vcm_light_shade_kernel(const DeviceShading S, const VcmParams* Pd, const DevCamera cam, float4* rays, const int4* hits, VCMState* states,
                                                               const int* sorted, const int* hit_count_ptr, const int* queue_count_ptr, float4* shadow_rays,
                                                               ShadowState* shadow_states, DevLightVertex* cache, int cache_capacity, int* cache_last,
                                                               unsigned long long* ray_stats, float4* out_rays, VCMState* out_states, int* out_count) {
+    const VcmParams P = *Pd;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i == 0 && ray_stats) atomicAdd(ray_stats, (unsigned long long)*queue_count_ptr);
     if (i >= *hit_count_ptr) return;
@@ -301,7 +303,8 @@ __device__ __forceinline__ int grid_query(const GridParams& g, const int* cells,
 }
 
 /* ---- camera pass ---------------------------------------------------------------------------------------------- */
-__global__ void vcm_camera_raygen_kernel(DevCamera cam, VcmParams P, int spp, uint32_t seed_base, int count, float4* rays, VCMState* states, int* count_out) {
+__global__ void vcm_camera_raygen_kernel(DevCamera cam, const VcmParams* Pd, int spp, uint32_t seed_base, int count, float4* rays, VCMState* states, int* count_out) {
+    const VcmParams P = *Pd;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i == 0) *count_out = count;
     if (i >= count) return;
@@ -323,11 +326,12 @@ __global__ void vcm_camera_raygen_kernel(DevCamera cam, VcmParams P, int spp, ui
 }
 
 template <int ALGO>
-__global__ void __launch_bounds__(128) vcm_camera_shade_kernel(const DeviceShading S, const VcmParams P, float4* rays, const int4* hits, VCMState* states, const int* sorted,
+__global__ void __launch_bounds__(128) vcm_camera_shade_kernel(const DeviceShading S, const VcmParams* Pd, float4* rays, const int4* hits, VCMState* states, const int* sorted,
                                                                const int* hit_count_ptr, const int* queue_count_ptr, float4* shadow_rays, ShadowState* shadow_states,
                                                                const DevLightVertex* cache, const GridParams* gp, const int* cells, unsigned table,
                                                                const DevPhoton* photons, float* fb, unsigned long long* ray_stats, float4* out_rays, VCMState* out_states,
                                                                int* out_count) {
+    const VcmParams P = *Pd;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i == 0 && ray_stats) atomicAdd(ray_stats, (unsigned long long)*queue_count_ptr);
     if (i >= *hit_count_ptr) return;
@@ -464,11 +468,11 @@ cudaError_t camera_shade(const VcmLaunch& a, cudaStream_t st) {
 
 } // namespace
 
-cudaError_t imba_vcm_light_raygen(const DeviceShading& S, const VcmParams& P, uint32_t seed_base, int count, float4* rays, VCMState* states, int* count_out, cudaStream_t st) {
+cudaError_t imba_vcm_light_raygen(const DeviceShading& S, const VcmParams* P, uint32_t seed_base, int count, float4* rays, VCMState* states, int* count_out, cudaStream_t st) {
     vcm_light_raygen_kernel<<<(std::max(count, 1) + 255) / 256, 256, 0, st>>>(S, P, seed_base, count, rays, states, count_out);
     return cudaGetLastError();
 }
-cudaError_t imba_vcm_camera_raygen(const DevCamera& cam, const VcmParams& P, int spp, uint32_t seed_base, int count, float4* rays, VCMState* states, int* count_out, cudaStream_t st) {
+cudaError_t imba_vcm_camera_raygen(const DevCamera& cam, const VcmParams* P, int spp, uint32_t seed_base, int count, float4* rays, VCMState* states, int* count_out, cudaStream_t st) {
     vcm_camera_raygen_kernel<<<(std::max(count, 1) + 255) / 256, 256, 0, st>>>(cam, P, spp, seed_base, count, rays, states, count_out);
     return cudaGetLastError();
 }

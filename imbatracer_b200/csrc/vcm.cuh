@@ -15,7 +15,7 @@ struct GridParams {           // HashGrid members (rangesearch.h:148-156) + the 
     int   count;
 };
 struct VcmLaunch {
-    const DeviceShading* S; VcmParams P; DevCamera cam;
+    const DeviceShading* S; const VcmParams* P; DevCamera cam;   // P lives in device memory: launches (and captured graphs) stay valid across iterations
     float4* rays; const int4* hits; VCMState* states; const int* sorted; const int* hit_count_ptr; const int* queue_count_ptr; int capacity;
     float4* shadow_rays; ShadowState* shadow_states;
     DevLightVertex* cache; int cache_capacity; int* cache_last;
@@ -24,8 +24,8 @@ struct VcmLaunch {
     float4* out_rays; VCMState* out_states; int* out_count; // next wavefront's queue (fused compaction)
 };
 
-cudaError_t imba_vcm_light_raygen(const DeviceShading& S, const VcmParams& P, uint32_t seed_base, int count, float4* rays, VCMState* states, int* count_out, cudaStream_t st);
-cudaError_t imba_vcm_camera_raygen(const DevCamera& cam, const VcmParams& P, int spp, uint32_t seed_base, int count, float4* rays, VCMState* states, int* count_out, cudaStream_t st);
+cudaError_t imba_vcm_light_raygen(const DeviceShading& S, const VcmParams* P, uint32_t seed_base, int count, float4* rays, VCMState* states, int* count_out, cudaStream_t st);
+cudaError_t imba_vcm_camera_raygen(const DevCamera& cam, const VcmParams* P, int spp, uint32_t seed_base, int count, float4* rays, VCMState* states, int* count_out, cudaStream_t st);
 cudaError_t imba_vcm_light_shade(int algo, const VcmLaunch& a, cudaStream_t st);
 cudaError_t imba_vcm_camera_shade(int algo, const VcmLaunch& a, cudaStream_t st);
 cudaError_t imba_grid_build(const DevLightVertex* cache, const int* cache_last, int cache_capacity, float radius, GridParams* grid, int* bbox, int* cells, unsigned table,

@@ -7,6 +7,7 @@
  * every wavefront of the light pass.  The camera pass is capped by max_path_len and is enqueued without host sync.
  */
 #include "vcm.cuh"
+#include <cstdlib>
 
 static VcmParams iteration_params(const imba_integrator* it, uint64_t iteration_1based) {
     // vcm.cpp:28-46
@@ -23,10 +24,10 @@ static VcmParams iteration_params(const imba_integrator* it, uint64_t iteration_
     return P;
 }
 
-static VcmLaunch base_launch(imba_integrator* it, const VcmParams& P, int cur, int capacity) {
+static VcmLaunch base_launch(imba_integrator* it, int cur, int capacity) {
     const DeviceShading* S = imba_shading_view(it->scene);
     VcmLaunch a;
-    a.S = S; a.P = P; a.cam = it->cam;
+    a.S = S; a.P = it->d_params; a.cam = it->cam;
     a.rays = it->rays[cur]; a.hits = it->hits; a.states = (VCMState*)it->states[cur]; a.sorted = it->part.indices;
     a.hit_count_ptr = it->part.bin_start + S->material_count; a.queue_count_ptr = it->count[cur]; a.capacity = capacity;
     a.shadow_rays = it->shadow_rays; a.shadow_states = it->shadow_states;
@@ -38,20 +39,22 @@ static VcmLaunch base_launch(imba_integrator* it, const VcmParams& P, int cur, i
 }
 
 /* One wavefront of the light pass (light != 0) or of the camera pass. */
-static int vcm_wavefront(imba_integrator* it, const VcmParams& P, int algo, bool light, int cur, int capacity) {
+static int vcm_wavefront(imba_integrator* it, int algo, bool light, int cur, int capacity) {
     const DeviceShading& S = *imba_shading_view(it->scene);
     const int slots = light ? 1 : it->shadow_slots;
     TraceRequest rq; rq.d_rays = (const imba_ray*)it->rays[cur]; rq.d_hits = (imba_hit*)it->hits; rq.capacity = capacity; rq.d_count = it->count[cur]; rq.mode = 0;
+    if (it->tail_counter_next >= 0) rq.d_work_counter = it->tail_counters + it->tail_counter_next++;
     int rc = imba_scene_trace_ex(it->scene, rq, it->stream);
     if (rc != IMBA_OK) return rc;
     IMBA_CUDA(imba_sort_hits_by_material(it->part, it->hits, S.indices, S.material_count, (int*)it->shadow_states, slots, it->count[cur], 0, capacity, it->stream, false), IMBA_ERR_CUDA);
     IMBA_CUDA(cudaMemsetAsync(it->count[cur ^ 1], 0, sizeof(int), it->stream), IMBA_ERR_CUDA);
-    const VcmLaunch a = base_launch(it, P, cur, capacity);
+    const VcmLaunch a = base_launch(it, cur, capacity);
     IMBA_CUDA(light ? imba_vcm_light_shade(algo, a, it->stream) : imba_vcm_camera_shade(algo, a, it->stream), IMBA_ERR_CUDA);
     const bool shadows = light ? algo != IMBA_ALGO_PPM : algo != IMBA_ALGO_PPM; // PPM emits no shadow rays in either pass
     if (shadows) {
         TraceRequest sq; sq.d_rays = (const imba_ray*)it->shadow_rays; sq.capacity = capacity * slots; sq.d_count = it->count[cur]; sq.count_mul = slots; sq.mode = 2;
         sq.d_shadow_states = it->shadow_states; sq.d_framebuffer = it->fb;
+        if (it->tail_counter_next >= 0) sq.d_work_counter = it->tail_counters + it->tail_counter_next++;
         rc = imba_scene_trace_ex(it->scene, sq, it->stream);
         if (rc != IMBA_OK) return rc;
     }
@@ -60,26 +63,69 @@ static int vcm_wavefront(imba_integrator* it, const VcmParams& P, int algo, bool
     return IMBA_OK;
 }
 
+static int set_params(imba_integrator* it, const VcmParams& P) {
+    IMBA_CUDA(cudaMemcpyAsync(it->d_params, &P, sizeof(P), cudaMemcpyHostToDevice, it->stream), IMBA_ERR_CUDA);
+    IMBA_CUDA(cudaStreamSynchronize(it->stream), IMBA_ERR_CUDA); // P is a stack variable of the caller
+    return IMBA_OK;
+}
+
+constexpr int TAIL_RAYS = 65536, TAIL_WAVES = 32;
+
+/* Light paths have no length cap (vcm.cpp:133-139): in scenes with glass a few paths bounce hundreds of times.  Once the
+ * queue is small the wavefront is launch-bound, so TAIL_WAVES wavefronts (sized for TAIL_RAYS rays, counts in device
+ * memory) are captured once into a CUDA graph and replayed until the queue is empty. */
+static int build_tail_graph(imba_integrator* it, int algo) {
+    cudaGraph_t graph = nullptr;
+    if (!it->tail_counters) IMBA_CUDA(cudaMalloc((void**)&it->tail_counters, sizeof(unsigned) * 2 * TAIL_WAVES), IMBA_ERR_CUDA);
+    it->tail_counter_next = 0;
+    IMBA_CUDA(cudaStreamBeginCapture(it->stream, cudaStreamCaptureModeThreadLocal), IMBA_ERR_CUDA);
+    int rc = IMBA_OK, cur = 0;
+    for (int k = 0; k < TAIL_WAVES && rc == IMBA_OK; ++k, cur ^= 1) rc = vcm_wavefront(it, algo, true, cur, TAIL_RAYS);
+    const cudaError_t e = cudaStreamEndCapture(it->stream, &graph);
+    it->tail_counter_next = -1;
+    if (rc != IMBA_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+    IMBA_CUDA(e, IMBA_ERR_CUDA);
+    const cudaError_t e2 = cudaGraphInstantiate(&it->tail_graph, graph, 0);
+    cudaGraphDestroy(graph);
+    IMBA_CUDA(e2, IMBA_ERR_CUDA);
+    return IMBA_OK;
+}
+
 /* Traces all light paths of one iteration; returns the number of wavefronts through *waves. */
-static int light_pass(imba_integrator* it, const VcmParams& P, int algo, uint32_t seed_base, int path_count, int* waves) {
+static int light_pass(imba_integrator* it, int algo, uint32_t seed_base, int path_count, int* waves, bool use_graph) {
     const DeviceShading& S = *imba_shading_view(it->scene);
     IMBA_CUDA(cudaMemsetAsync(it->cache_last, 0, sizeof(int), it->stream), IMBA_ERR_CUDA);
-    IMBA_CUDA(imba_vcm_light_raygen(S, P, seed_base, path_count, it->rays[0], (VCMState*)it->states[0], it->count[0], it->stream), IMBA_ERR_CUDA);
+    IMBA_CUDA(imba_vcm_light_raygen(S, it->d_params, seed_base, path_count, it->rays[0], (VCMState*)it->states[0], it->count[0], it->stream), IMBA_ERR_CUDA);
     g_imba_launches.fetch_add(1);
-    int cur = 0, n = path_count, w = 0;
+    // The queue size is read back only every `batch` wavefronts (the grid stays sized for the last known count; kernels on
+    // an already empty queue return at once), so long light paths do not cost one host round trip per bounce.
+    int cur = 0, n = path_count, w = 0, batch = 2;
     while (n > 0) {
-        const int rc = vcm_wavefront(it, P, algo, true, cur, n);
-        if (rc != IMBA_OK) return rc;
-        cur ^= 1; ++w;
+        if (use_graph && n <= TAIL_RAYS && cur == 0) {
+            if (!it->tail_graph) { const int rc = build_tail_graph(it, algo); if (rc != IMBA_OK) return rc; }
+            IMBA_CUDA(cudaGraphLaunch(it->tail_graph, it->stream), IMBA_ERR_CUDA);
+            g_imba_launches.fetch_add(TAIL_WAVES * 6);
+            w += TAIL_WAVES; // an even number of wavefronts: the live queue is queue 0 again
+        } else {
+            const int k_end = (use_graph && n <= TAIL_RAYS) ? 1 : batch; // make the parity even before switching to the graph
+            for (int k = 0; k < k_end; ++k, cur ^= 1, ++w) {
+                const int rc = vcm_wavefront(it, algo, true, cur, n);
+                if (rc != IMBA_OK) return rc;
+            }
+            if (batch < 16) batch *= 2;
+        }
         IMBA_CUDA(cudaMemcpyAsync(&n, it->count[cur], sizeof(int), cudaMemcpyDeviceToHost, it->stream), IMBA_ERR_CUDA);
         IMBA_CUDA(cudaStreamSynchronize(it->stream), IMBA_ERR_CUDA);
-        if (w > 4096) { imba_set_error("light pass did not terminate"); return IMBA_ERR_OVERFLOW; }
+        if (w > 65536) { imba_set_error("light pass did not terminate"); return IMBA_ERR_OVERFLOW; }
     }
     if (waves) *waves = w;
+    if (getenv("IMBA_VERBOSE")) fprintf(stderr, "[imba] light pass: %d paths, %d wavefronts\n", path_count, w);
     return IMBA_OK;
 }
 
 void imba_vcm_free(imba_integrator* it) {
+    if (it->tail_graph) { cudaGraphExecDestroy(it->tail_graph); it->tail_graph = nullptr; }
+    cudaFree(it->d_params); it->d_params = nullptr; cudaFree(it->tail_counters); it->tail_counters = nullptr;
     cudaFree(it->cache); cudaFree(it->cache_last); cudaFree(it->grid); cudaFree(it->grid_bbox); cudaFree(it->cells); cudaFree(it->block_sums); cudaFree(it->photons);
     it->cache = nullptr; it->cache_last = nullptr; it->grid = nullptr; it->grid_bbox = nullptr; it->cells = nullptr; it->block_sums = nullptr; it->photons = nullptr;
 }
@@ -89,6 +135,7 @@ int imba_vcm_allocate(imba_integrator* it) {
     const int cap = std::max(it->cache_capacity, 1);
     it->table = (unsigned)cap * 2u; // inv_load_factor = 2 (rangesearch.h:26)
     bool ok = cudaMalloc((void**)&it->cache, (size_t)cap * sizeof(DevLightVertex)) == cudaSuccess;
+    ok = ok && cudaMalloc((void**)&it->d_params, sizeof(VcmParams)) == cudaSuccess;
     ok = ok && cudaMalloc((void**)&it->cache_last, 16) == cudaSuccess && cudaMemset(it->cache_last, 0, 16) == cudaSuccess;
     ok = ok && cudaMalloc((void**)&it->grid, sizeof(GridParams)) == cudaSuccess && cudaMemset(it->grid, 0, sizeof(GridParams)) == cudaSuccess;
     ok = ok && cudaMalloc((void**)&it->grid_bbox, 32) == cudaSuccess;
@@ -112,13 +159,15 @@ int imba_vcm_preprocess(imba_integrator* it) {
     int rc = imba_vcm_allocate(it);
     if (rc != IMBA_OK) return rc;
     VcmParams P = iteration_params(it, 1);
+    rc = set_params(it, P);
+    if (rc != IMBA_OK) return rc;
     float* saved_fb = it->fb; // the probe must not contribute: let its camera connections go to a scratch accumulator
     float* scratch = nullptr;
     IMBA_CUDA(cudaMalloc((void**)&scratch, (size_t)it->cfg.width * it->cfg.height * 3 * sizeof(float)), IMBA_ERR_CUDA);
     it->fb = scratch;
     unsigned long long stats[2];
     IMBA_CUDA(cudaMemcpy(stats, it->d_stats, 16, cudaMemcpyDeviceToHost), IMBA_ERR_CUDA);
-    rc = light_pass(it, P, IMBA_ALGO_PPM /* cache appends only */, imba_iteration_seed(it->cfg.seed, ~0ull, 3), probes, nullptr);
+    rc = light_pass(it, IMBA_ALGO_PPM /* cache appends only */, imba_iteration_seed(it->cfg.seed, ~0ull, 3), probes, nullptr, false);
     it->fb = saved_fb; cudaFree(scratch);
     if (rc != IMBA_OK) return rc;
     IMBA_CUDA(cudaMemcpy(it->d_stats, stats, 16, cudaMemcpyHostToDevice), IMBA_ERR_CUDA);
@@ -138,9 +187,10 @@ int imba_vcm_render_iteration(imba_integrator* it) {
     const uint64_t global_iter = it->iteration * (uint64_t)it->cfg.rank_count + (uint64_t)it->cfg.rank;
     // the radius schedule follows the GLOBAL iteration index when iterations are sharded over ranks
     const VcmParams P = iteration_params(it, global_iter + 1);
-    int rc;
+    int rc = set_params(it, P);
+    if (rc != IMBA_OK) return rc;
     if (algo != IMBA_ALGO_VCM_PT) {
-        rc = light_pass(it, P, algo, imba_iteration_seed(it->cfg.seed, global_iter, 1), it->cfg.light_path_count, nullptr);
+        rc = light_pass(it, algo, imba_iteration_seed(it->cfg.seed, global_iter, 1), it->cfg.light_path_count, nullptr, !getenv("IMBA_NO_GRAPH"));
         if (rc != IMBA_OK) return rc;
         if (algo != IMBA_ALGO_LT) { // light_vertices_.build(pm_radius_, algo != ALGO_BPT), vcm.cpp:98-99
             IMBA_CUDA(imba_grid_build(it->cache, it->cache_last, it->cache_capacity, P.pm_radius, it->grid, it->grid_bbox, it->cells, it->table, it->block_sums,
@@ -149,12 +199,12 @@ int imba_vcm_render_iteration(imba_integrator* it) {
         }
     }
     if (algo != IMBA_ALGO_LT) {
-        IMBA_CUDA(imba_vcm_camera_raygen(it->cam, P, it->cfg.spp, imba_iteration_seed(it->cfg.seed, global_iter, 2), it->pixel_capacity, it->rays[0],
+        IMBA_CUDA(imba_vcm_camera_raygen(it->cam, it->d_params, it->cfg.spp, imba_iteration_seed(it->cfg.seed, global_iter, 2), it->pixel_capacity, it->rays[0],
                                          (VCMState*)it->states[0], it->count[0], it->stream), IMBA_ERR_CUDA);
         g_imba_launches.fetch_add(1);
         int cur = 0;
         for (int wave = 0; wave < it->cfg.max_path_len; ++wave, cur ^= 1) {
-            rc = vcm_wavefront(it, P, algo, false, cur, it->pixel_capacity);
+            rc = vcm_wavefront(it, algo, false, cur, it->pixel_capacity);
             if (rc != IMBA_OK) return rc;
         }
     }

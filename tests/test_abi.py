@@ -55,3 +55,15 @@ def test_primary_ray_seeding_matches_reference_known_answers():
     out = np.zeros(4096, np.uint64)
     abi.check(abi.lib().imba_seed_states(0x1234ABCD, 0, 4096, 4, out.ctypes.data))
     assert np.array_equal(out, k["seed_states"])
+
+
+def test_cpp_host_mirror_compiles_links_and_refuses_without_gpu(tmp_path):
+    """include/imba_b200.hpp (RayQueue / Integrator mirror of ray_queue.h, integrator.h) builds with the host compiler and
+    links against the product library; on a box without a GPU the library refuses instead of falling back."""
+    import subprocess
+    exe = str(tmp_path / "host_mirror_test")
+    lib_dir = os.path.dirname(abi.LIB_PATH)
+    subprocess.run(["/usr/bin/g++", "-std=c++11", "-Wall", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "cpp", "host_mirror_test.cpp"),
+                    "-o", exe, "-L", lib_dir, "-limba_b200", f"-Wl,-rpath,{lib_dir}"], check=True)
+    r = subprocess.run([exe], stdout=subprocess.PIPE, text=True)
+    assert r.returncode in (0, 2), (r.returncode, r.stdout)
