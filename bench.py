@@ -192,27 +192,15 @@ def run_pt(scene, flat, rank, world, barrier, dist, iters, width=1920, height=10
     import torch
     from imbatracer_b200 import api
     integ = api.Integrator(scene, api.render_settings(flat, "pt", width, height, spp=1, max_path_len=10, seed=0x1234ABCD, rank=rank, rank_count=world))
-    fb = torch.zeros(width * height * 3, dtype=torch.float32, device="cuda")
-    integ.set_framebuffer(fb)
+    from imbatracer_b200.distributed import ProgressiveRenderer
     integ.preprocess()
-    stream = torch.cuda.ExternalStream(integ.stream_ptr())
-    total = torch.zeros_like(fb)
-
-    def iteration():
-        integ.render(1)
-        if dist is not None:
-            with torch.cuda.stream(stream):
-                dist.all_reduce(fb)          # every rank ends up with the sum of all ranks' samples of this iteration
-        with torch.cuda.stream(stream):
-            total.add_(fb); fb.zero_()
-
-    for _ in range(2):
-        iteration()
+    loop = ProgressiveRenderer(integ, width, height)   # integ.render(1) + NCCL sum of the framebuffer, per iteration
+    stream = loop.stream
+    loop.step(2)
     integ.sync(); barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
-    for _ in range(iters):
-        iteration()
+    loop.step(iters)
     e1.record(stream)
     integ.sync(); barrier()
     ms = e0.elapsed_time(e1)
@@ -220,6 +208,7 @@ def run_pt(scene, flat, rank, world, barrier, dist, iters, width=1920, height=10
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t[0])
+    total = loop.total
     prim, shad = integ.ray_counts()
     mean = float(total.mean()) / ((iters + 2) * world)
     integ.close()

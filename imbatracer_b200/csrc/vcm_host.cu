@@ -80,7 +80,7 @@ static int build_tail_graph(imba_integrator* it, int algo) {
     it->tail_counter_next = 0;
     IMBA_CUDA(cudaStreamBeginCapture(it->stream, cudaStreamCaptureModeThreadLocal), IMBA_ERR_CUDA);
     int rc = IMBA_OK, cur = 0;
-    for (int k = 0; k < TAIL_WAVES && rc == IMBA_OK; ++k, cur ^= 1) rc = vcm_wavefront(it, algo, true, cur, TAIL_RAYS);
+    for (int k = 0; k < TAIL_WAVES && rc == IMBA_OK; ++k, cur ^= 1) rc = vcm_wavefront(it, algo, true, cur, std::min(TAIL_RAYS, it->capacity));
     const cudaError_t e = cudaStreamEndCapture(it->stream, &graph);
     it->tail_counter_next = -1;
     if (rc != IMBA_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
@@ -101,13 +101,14 @@ static int light_pass(imba_integrator* it, int algo, uint32_t seed_base, int pat
     // an already empty queue return at once), so long light paths do not cost one host round trip per bounce.
     int cur = 0, n = path_count, w = 0, batch = 2;
     while (n > 0) {
-        if (use_graph && n <= TAIL_RAYS && cur == 0) {
+        const int tail_rays = std::min(TAIL_RAYS, it->capacity);
+        if (use_graph && n <= tail_rays && cur == 0) {
             if (!it->tail_graph) { const int rc = build_tail_graph(it, algo); if (rc != IMBA_OK) return rc; }
             IMBA_CUDA(cudaGraphLaunch(it->tail_graph, it->stream), IMBA_ERR_CUDA);
             g_imba_launches.fetch_add(TAIL_WAVES * 6);
             w += TAIL_WAVES; // an even number of wavefronts: the live queue is queue 0 again
         } else {
-            const int k_end = (use_graph && n <= TAIL_RAYS) ? 1 : batch; // make the parity even before switching to the graph
+            const int k_end = (use_graph && n <= tail_rays) ? 1 : batch; // make the parity even before switching to the graph
             for (int k = 0; k < k_end; ++k, cur ^= 1, ++w) {
                 const int rc = vcm_wavefront(it, algo, true, cur, n);
                 if (rc != IMBA_OK) return rc;

@@ -112,3 +112,23 @@ def test_queue_primitives_match_numpy(torch_device=None):
         assert o_rays.cpu().numpy().view(abi.RAY).tobytes() == rays[order].tobytes()
         assert o_states.cpu().numpy().view(abi.PT_STATE).tobytes() == states[order].tobytes()
     sc.close()
+
+
+def test_headless_driver_prints_reference_report_line_and_matches_golden(tmp_path):
+    """python -m imbatracer_b200.render = frontend/main.cpp minus SDL: same flags, same final line, PNG like store_png.h."""
+    import re
+    import subprocess
+    import sys
+    from tests.conftest import ROOT
+    from PIL import Image
+    out = str(tmp_path / "cornell.png")
+    golden = np.load(os.path.join(GOLDEN, "ref_cornell_org_128.npy"))
+    ref_png = str(tmp_path / "ref.png")
+    Image.fromarray((255.0 * np.clip(golden, 0, 1) ** 0.5).astype(np.uint8)).save(ref_png)
+    r = subprocess.run([sys.executable, "-m", "imbatracer_b200.render", os.path.join(GOLDEN, "scene_cornell_org_gpu.npz"), out, "-a", "pt", "-w", "128",
+                        "-h", "128", "-s", "128", "-q", "--compare", ref_png], cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    m = re.search(r"Done after ([\d.e+-]+) seconds, (\d+) samples @ ([\d.e+-]+) frames per second", r.stdout)  # test/run_bench.py:207
+    assert m and int(m.group(2)) == 128
+    rmse = float(re.search(r"RMSE ([\d.e+-]+)", r.stdout).group(1))
+    assert rmse < 0.05 and os.path.exists(out)
