@@ -123,6 +123,9 @@ def lib():
     L.imba_bvh8_arrays.argtypes = [vp, C.POINTER(vp), C.POINTER(i64), C.POINTER(vp), C.POINTER(i64), C.POINTER(vp),
                                    C.POINTER(i64), C.POINTER(C.c_uint32), C.POINTER(i32)]
     f32, u32 = C.c_float, C.c_uint32
+    L.imba_accel_build.restype = vp; L.imba_accel_build.argtypes = [C.POINTER(SceneDesc)]
+    L.imba_accel_free.restype = None; L.imba_accel_free.argtypes = [vp]
+    L.imba_accel_arrays.argtypes = [vp, C.POINTER(vp), C.POINTER(i64), C.POINTER(vp), C.POINTER(i64), C.POINTER(vp), C.POINTER(i64), C.POINTER(i32)]
     L.imba_integrator_create.restype = vp; L.imba_integrator_create.argtypes = [vp, C.POINTER(RenderSettings)]
     L.imba_integrator_destroy.restype = None; L.imba_integrator_destroy.argtypes = [vp]
     L.imba_integrator_preprocess.argtypes = [vp]

@@ -212,6 +212,17 @@ void imba_bvh8_free(imba_bvh8* h);
 int  imba_bvh8_arrays(const imba_bvh8* h, const void** nodes, int64_t* node_count, const void** tris, int64_t* tri_count,
                       const void** insts, int64_t* inst_count, uint32_t* top_root, int32_t* max_depth);
 
+/* Host builder of the two-level structure in the reference's BVH2 layout for scenes that come without one (procedural
+ * scenes): binned SAH per mesh and over the instance boxes, emitted exactly as core/gpu_adapter.cpp / render/scene.cpp:
+ * 168-176 lay it out, so it feeds imba_scene_create (and the CPU oracle) like a reference-built structure.  Uses
+ * mesh_*, vertices, indices, instances of `desc`; imba_accel_fill points desc's accel fields at the result. */
+typedef struct imba_accel imba_accel;
+imba_accel* imba_accel_build(const imba_scene_desc* desc);
+int  imba_accel_fill(const imba_accel* a, imba_scene_desc* desc);
+int  imba_accel_arrays(const imba_accel* a, const void** nodes, int64_t* node_count, const void** tris, int64_t* tri_vec4_count,
+                       const void** inst_nodes, int64_t* inst_node_count, int32_t* root);
+void imba_accel_free(imba_accel* a);
+
 /* ------------------------------------------------------------------------------------------
  * L2: ray-queue primitives on device arrays (render/scheduling/ray_queue.h:161-244)
  * ---------------------------------------------------------------------------------------- */

@@ -384,6 +384,43 @@ int ref_calc_intersections(void* h, int count, const imba_ray* rays, const imba_
     return 0;
 }
 
+/// TEST HOOK: gives the (texture-less) Cornell scenes procedural textures, bump maps and texture coordinates so that the
+/// reference's TextureSampler::sample (texture_sampler.h:18-46), Material::bump (materials.h:34-55) and the textured
+/// branches of DiffuseMaterial / GlossyMaterial::get_bsdf run in the parity harness.  Every non-emissive diffuse material
+/// gets a colour texture, every second one a bump map, glossy materials a diffuse texture; vertices get seeded texcoords.
+int ref_scene_add_test_textures(void* h, uint64_t seed) {
+    auto rs = (RefScene*)h; Scene& sc = *rs->scene;
+    RNG rng(seed);
+    auto make_tex = [&](int w, int hgt, bool smooth) -> TextureSampler* {
+        Image img(w, hgt);
+        for (int i = 0; i < w * hgt; ++i) {
+            const float a = rng.random_float(), b = rng.random_float(), c = rng.random_float();
+            img.pixels()[i] = smooth ? rgba(0.5f + 0.5f * sinf(0.7f * i), a * 0.2f, b, 1.0f) : rgba(0.2f + 0.8f * a, 0.2f + 0.8f * b, 0.2f + 0.8f * c, 1.0f);
+        }
+        sc.textures().emplace_back(new TextureSampler(std::move(img)));
+        return sc.textures().back().get();
+    };
+    int changed = 0;
+    for (size_t m = 0; m < sc.material_count(); ++m) {
+        Material* mat = sc.material(m).get();
+        if (mat->emitter()) continue;
+        if (dynamic_cast<DiffuseMaterial*>(mat)) {
+            TextureSampler* col = make_tex(7 + (int)m, 5 + (int)m % 3, false);
+            TextureSampler* bump = (m % 2 == 0) ? make_tex(16, 9, true) : nullptr;
+            sc.materials()[m].reset(new DiffuseMaterial(col, bump)); ++changed;
+        } else if (auto g = dynamic_cast<GlossyMaterial*>(mat)) {
+            TextureSampler* col = make_tex(11, 13, false);
+            sc.materials()[m].reset(new GlossyMaterial(g->exponent_, g->specular_color_, col, make_tex(8, 8, true))); ++changed;
+        }
+    }
+    for (size_t k = 0; k < sc.mesh_count(); ++k) {
+        Mesh& mesh = sc.meshes()[k];
+        auto tc = mesh.attribute<float2>(MeshAttributes::TEXCOORDS);
+        for (size_t v = 0; v < mesh.vertex_count(); ++v) { tc[v].x = 4.0f * rng.random_float() - 1.5f; tc[v].y = 4.0f * rng.random_float() - 1.5f; }
+    }
+    return changed;
+}
+
 /// RNG known-answer helper (render/random.h:15-47).
 void ref_rng_floats(uint64_t seed, int discard, int n, float* out, uint64_t* state_out) {
     RNG rng(seed); rng.discard(discard);

@@ -61,6 +61,7 @@ def ref():
         L.ref_rng_floats.restype = None; L.ref_rng_floats.argtypes = [C.c_uint64, i32, i32, vp, vp]
         L.ref_seed_states.restype = None; L.ref_seed_states.argtypes = [C.c_uint64, i32, i32, i32, vp]
         L.ref_struct_sizes.argtypes = [vp]
+        L.ref_scene_add_test_textures.argtypes = [vp, C.c_uint64]
         _ref = L
     return _ref
 
@@ -137,6 +138,10 @@ class RefScene:
     def close(self):
         if self.h:
             self.L.ref_scene_free(self.h); self.h = None
+
+    def add_test_textures(self, seed=99):
+        """Procedural colour / bump textures + texcoords on the reference side (oracle/ref_driver.cpp); export with flat() afterwards."""
+        return self.L.ref_scene_add_test_textures(self.h, seed)
 
     def flat(self, name="") -> FlatScene:
         d = abi.SceneDesc()

@@ -36,6 +36,23 @@ def test_pt_shading_stage_matches_reference_wavefronts(scene):
         assert r["fb_max_abs_err"] <= 1e-4 * max(1.0, r["fb_ref_sum"]), r
 
 
+@needs_ref
+@pytest.mark.parametrize("scene", ["cornell_org", "cornell_specular_front"])
+def test_textured_and_bump_mapped_shading_matches_reference(scene):
+    """TextureSampler::sample (texture_sampler.h:18-46), Material::bump (materials.h:34-55) and the textured get_bsdf
+    branches: procedural textures / bump maps / texcoords are injected into the reference's scene, exported, and both
+    sides shade the same wavefronts."""
+    from tests import shading_harness as sh
+    res = sh.run_waves(scene, w=96, h=96, waves=4, textured=True)
+    for r in res[1:]:
+        assert r["ref_cont"] == r["dev_cont"] and r["ref_shadow"] == r["dev_shadow"], r
+        if r["ref_cont"]:
+            assert r["cont_same_order"] and r["cont_rng_equal"] == 1.0 and r["cont_flags_equal"] == 1.0, r
+            assert r["cont_close"] >= 0.995, r
+        if r["ref_shadow"]:
+            assert r["shadow_close"] >= 0.995, r
+
+
 def gamma_rmse(a, b):
     return float(np.sqrt(np.mean((np.clip(a, 0, 1) ** 0.5 - np.clip(b, 0, 1) ** 0.5) ** 2)))
 
