@@ -218,6 +218,49 @@ def run_pt(scene, flat, rank, world, barrier, dist, iters, width=1920, height=10
             "framebuffer_allreduce_bytes": width * height * 12 if dist is not None else 0, "mean_radiance": mean}
 
 
+def run_extra_scenes(rank):
+    """configs[4] and a memory-bound case (rank 0 only, after the timed regions): incoherent traversal on the procedural
+    ~19 M-triangle instanced scene and on a 4.7 M-triangle unique terrain (292 MB of nodes + triangles, > L2), plus VCM with
+    photon merging on the instanced scene.  Structures built by the product's host builder (csrc/accel_build.cpp)."""
+    import torch
+    from imbatracer_b200 import api, procedural
+    from tests import raygen
+    out = {}
+    base = load_flat()
+    n = 1 << 22
+    for label, make in (("instanced_19M", lambda: procedural.instanced_grid(base, 14, 14, 14)), ("terrain_4.7M", lambda: procedural.terrain(1536))):
+        flat = make()
+        scene = api.Scene(flat)
+        rays = raygen.random_rays(flat, n, 11, tmax_mix=False); rays["tmin"] = 0
+        d = api.rays_to_device(rays); hits = torch.empty((n, 4), dtype=torch.int32, device="cuda")
+        cnt = torch.zeros((n, 4), dtype=torch.int32, device="cuda")
+        scene.trace(d, hits, counters=cnt); torch.cuda.synchronize()
+        c = cnt.double().mean(0).cpu().numpy()
+        r = {"triangles_unique": int(flat.tri_count), "instances": int(len(flat.instances)), "bvh8_bytes": int(scene.stats()["bytes"])}
+        for any_hit in (0, 1):
+            for _ in range(3):
+                scene.trace(d, hits, any_hit=bool(any_hit))
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(5):
+                scene.trace(d, hits, any_hit=bool(any_hit))
+            e1.record(); torch.cuda.synchronize()
+            r["occluded_mrays_s" if any_hit else "closest_mrays_s"] = n * 5 / e0.elapsed_time(e1) / 1e3
+        bpr = 48 + 80 * c[0] + 48 * c[1] + 64 * c[2]
+        r.update({"nodes_per_ray": c[0], "tris_per_ray": c[1], "instances_per_ray": c[2], "bytes_per_ray": bpr,
+                  "algorithmic_gb_s": r["closest_mrays_s"] * 1e6 * bpr / 1e9, "rays": "4 Mi uniformly random rays in the bounding sphere"})
+        if label.startswith("instanced"):
+            integ = api.Integrator(scene, api.render_settings(flat, "vcm", 1280, 720, seed=3))
+            integ.preprocess(); integ.render(1); integ.sync()
+            t0 = time.perf_counter(); integ.render(4); integ.sync(); dt = time.perf_counter() - t0
+            r["vcm_1280x720"] = {"ms_per_iteration": dt / 4 * 1e3, "samples_per_s": 1280 * 720 * 4 / dt, "light_paths": 1280 * 720 // 2, "connections": 1, "knn": 10}
+            integ.close()
+        out[label] = r
+        scene.close()
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -316,7 +359,7 @@ def run_ours(args):
                         "steps": e2e_steps, "note": "imba_trace_host on pinned host queues, wall clock with device sync"},
                 "gpu_launches": int(launches),
                 "clocks": sampler.summary(),
-                "pt": pt,
+                "pt": pt, "scenes": run_extra_scenes(rank),
                 "per_kernel": {name: {"ms": per_kernel_ms[i], "mrays_s": n / per_kernel_ms[i] / 1e3} for i, (name, _) in enumerate(BATCH_ORDER)},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                              "kernel": "trace_kernel<closest> on the incoherent batch", "peak_source": peak_src,

@@ -86,7 +86,7 @@ def terrain(n=1024, seed=7, name="terrain"):
     """One unique mesh of 2*n*n triangles: a fractal height field over [-10, 10]^2 with four diffuse materials and two
     large triangle lights above it (stresses BVH size: ~128 bytes of nodes + triangles per triangle)."""
     rng = np.random.default_rng(seed)
-    xs = np.linspace(-10, 10, n + 1, dtype=np.float32)
+    xs = np.linspace(-10, 10, n + 1, dtype=np.float32) + np.float32(0.0137)  # keep grid lines off the coordinate planes
     X, Z = np.meshgrid(xs, xs, indexing="xy")
     H = np.zeros_like(X)
     for o in range(1, 7):

@@ -20,7 +20,7 @@ def random_rays(scene, n, seed, tmax_mix=True):
     return r
 
 
-def edge_rays(scene):
+def edge_rays(scene, vertex_rays=True):
     """Padding rays (all zero, ray_queue.h:74,250), axis-parallel rays with exact zeros of both signs, tmax = 0,
     rays starting on vertices, unnormalised directions."""
     c, rad = scene.bsphere[:3].astype(np.float32), np.float32(scene.bsphere[3])
@@ -39,7 +39,7 @@ def edge_rays(scene):
                     ax[k]["org"] = o; ax[k]["dir"] = d; ax[k]["tmax"] = np.finfo(np.float32).max; k += 1
     out.append(ax[:k])
     v = scene.vertices.reshape(-1, 4)[:, :3]
-    nv = min(len(v), 512)
+    nv = min(len(v), 512) if vertex_rays else 0
     rng = np.random.default_rng(7)
     vr = np.zeros(nv, abi.RAY)
     vr["org"] = v[:nv]
