@@ -124,6 +124,13 @@ int imba_scene_trace_ex(imba_scene* s, const TraceRequest& rq, cudaStream_t stre
     return IMBA_OK;
 }
 
+/* Scene part of the traversal arguments, for kernels that trace rays inline (traverse_core.cuh: trace_single). */
+void imba_scene_trace_args(const imba_scene* s, TraceArgs* a) {
+    memset(a, 0, sizeof(*a));
+    a->nodes = s->d_nodes; a->tris = s->d_tris; a->insts = s->d_insts; a->top_root = s->top_root; a->flat_inst = s->flat_inst;
+    a->indices = s->d_mask_indices; a->texcoords = s->d_mask_texcoords; a->masks = s->d_masks; a->mask_buffer = s->d_mask_buffer;
+}
+
 int imba_scene_trace(imba_scene* s, const imba_ray* d_rays, imba_hit* d_hits, int count, int any_hit, uint32_t* d_counters,
                      cudaStream_t stream) {
     if (count > 0 && !d_hits) { imba_set_error("invalid traversal arguments"); return IMBA_ERR_INVALID; }

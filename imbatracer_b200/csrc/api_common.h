@@ -58,6 +58,7 @@ struct TraceRequest {
     const void* d_shadow_states = nullptr; float* d_framebuffer = nullptr;
 };
 int imba_scene_trace_ex(imba_scene* s, const TraceRequest& rq, cudaStream_t stream);
+void imba_scene_trace_args(const imba_scene* s, TraceArgs* a);
 int imba_scene_trace(imba_scene* s, const imba_ray* d_rays, imba_hit* d_hits, int count, int any_hit, uint32_t* d_counters,
                      cudaStream_t stream);
 

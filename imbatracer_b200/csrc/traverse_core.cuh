@@ -1,0 +1,190 @@
+/* traverse_core.cuh -- the arithmetic of one traversal step, shared by the persistent wavefront kernel (traverse.cu) and
+ * by kernels that trace single rays inline (the light-path tail kernel, vcm.cu).  Every operation mirrors
+ * oracle/traversal_oracle.cpp; translation units including this header are compiled with -fmad=false. */
+#ifndef IMBA_TRAVERSE_CORE_CUH
+#define IMBA_TRAVERSE_CORE_CUH
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "bvh8.h"
+#include "kernels.h"
+
+__device__ __forceinline__ float safe_rcp(float d) {
+    return 1.0f / (fabsf(d) > IMBA_RCP_EPS ? d : copysignf(IMBA_RCP_EPS, d));
+}
+__device__ __forceinline__ uint32_t sign_extend_s8x4(uint32_t x) {
+    uint32_t r; asm("prmt.b32 %0, %1, 0, 0xBA98;" : "=r"(r) : "r"(x)); return r;
+}
+__device__ __forceinline__ float byte_f(uint32_t x, int j) { return (float)((x >> (8 * j)) & 0xffu); }
+__device__ __forceinline__ float dot_f(float ax, float ay, float az, float bx, float by, float bz) {
+    return __fmaf_rn(az, bz, __fmaf_rn(ay, by, ax * bx));
+}
+__device__ __forceinline__ float xorf(float f, uint32_t s) { return __uint_as_float(__float_as_uint(f) ^ s); }
+
+struct RayRegs {
+    float ox, oy, oz, dx, dy, dz, ix, iy, iz;
+    uint32_t octinv4;
+    __device__ __forceinline__ void finish() {
+        ix = safe_rcp(dx); iy = safe_rcp(dy); iz = safe_rcp(dz);
+        const uint32_t oct = (ix < 0.0f ? 4u : 0u) | (iy < 0.0f ? 2u : 0u) | (iz < 0.0f ? 1u : 0u);
+        octinv4 = (7u - oct) * 0x01010101u;
+    }
+};
+
+template <bool MASKS>
+__device__ __forceinline__ bool mask_opaque(const TraceArgs& P, int tri_id, float u, float v) {
+    if (!MASKS) return true;
+    const int mat = __ldg(P.indices + tri_id * 4 + 3);
+    const int mw = __ldg(P.masks + mat * 3), mh = __ldg(P.masks + mat * 3 + 1), mo = __ldg(P.masks + mat * 3 + 2);
+    if (mw == 1 && mh == 1 && mo == 0) return true;
+    const float2 a = __ldg(P.texcoords + __ldg(P.indices + tri_id * 4 + 0));
+    const float2 b = __ldg(P.texcoords + __ldg(P.indices + tri_id * 4 + 1));
+    const float2 c = __ldg(P.texcoords + __ldg(P.indices + tri_id * 4 + 2));
+    const float w = 1.0f - u - v;
+    float tu = a.x * w + b.x * u + c.x * v;
+    float tv = a.y * w + b.y * u + c.y * v;
+    tu = tu - floorf(tu);
+    tv = 1.0f - (tv - floorf(tv));
+    int x = (int)(tu * mw); if (x > mw - 1) x = mw - 1; if (x < 0) x = 0;
+    int y = (int)(tv * mh); if (y > mh - 1) y = mh - 1; if (y < 0) y = 0;
+    return P.mask_buffer[mo + y * mw + x] != 0;
+}
+
+
+struct HitRegs { float tbest, ubest; int tri_best, inst_best; };
+
+/* Intersects the 8 quantised child boxes of one node: returns the 8-bit inner / 24-bit primitive hit mask. */
+__device__ __forceinline__ uint32_t node_step(const uint4 n0, const uint4 n1, const uint4 n2, const uint4 n3, const uint4 n4, const RayRegs& r, float tmin, float tbest) {
+    const uint32_t e_imask = n0.w;
+    const float adjx = __uint_as_float((e_imask & 0xffu) << 23) * r.ix;
+    const float adjy = __uint_as_float(((e_imask >> 8) & 0xffu) << 23) * r.iy;
+    const float adjz = __uint_as_float(((e_imask >> 16) & 0xffu) << 23) * r.iz;
+    const float orgx = (__uint_as_float(n0.x) - r.ox) * r.ix;
+    const float orgy = (__uint_as_float(n0.y) - r.oy) * r.iy;
+    const float orgz = (__uint_as_float(n0.z) - r.oz) * r.iz;
+    uint32_t hitmask = 0;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        const uint32_t meta4 = half ? n1.w : n1.z;
+        const uint32_t is_inner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
+        const uint32_t inner_mask4 = sign_extend_s8x4(is_inner4 << 3);
+        const uint32_t bit_index4 = (meta4 ^ (r.octinv4 & inner_mask4)) & 0x1f1f1f1fu;
+        const uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
+        const uint32_t qlox = half ? n2.y : n2.x, qloy = half ? n2.w : n2.z, qloz = half ? n3.y : n3.x;
+        const uint32_t qhix = half ? n3.w : n3.z, qhiy = half ? n4.y : n4.x, qhiz = half ? n4.w : n4.z;
+        const uint32_t nx = r.ix < 0.0f ? qhix : qlox, fx = r.ix < 0.0f ? qlox : qhix;
+        const uint32_t ny = r.iy < 0.0f ? qhiy : qloy, fy = r.iy < 0.0f ? qloy : qhiy;
+        const uint32_t nz = r.iz < 0.0f ? qhiz : qloz, fz = r.iz < 0.0f ? qloz : qhiz;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float t0x = __fmaf_rn(byte_f(nx, j), adjx, orgx), t1x = __fmaf_rn(byte_f(fx, j), adjx, orgx);
+            const float t0y = __fmaf_rn(byte_f(ny, j), adjy, orgy), t1y = __fmaf_rn(byte_f(fy, j), adjy, orgy);
+            const float t0z = __fmaf_rn(byte_f(nz, j), adjz, orgz), t1z = __fmaf_rn(byte_f(fz, j), adjz, orgz);
+            const float tn = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, tmin));
+            const float tf = fminf(fminf(t1x, t1y), fminf(t1z, tbest));
+            if (tn <= tf * IMBA_ROBUST_TFAR) {
+                const uint32_t cb = (child_bits4 >> (8 * j)) & 0xffu, bi = (bit_index4 >> (8 * j)) & 0xffu;
+                hitmask |= cb << bi;
+            }
+        }
+    }
+    return hitmask;
+}
+
+/* Transforms the ray into instance space (cpu_adapter.cpp:356-365): t is shared between the levels (no renormalisation). */
+__device__ __forceinline__ void enter_instance(RayRegs& r, const float4 m0, const float4 m1, const float4 m2) {
+    const float ox = r.ox, oy = r.oy, oz = r.oz, dx = r.dx, dy = r.dy, dz = r.dz;
+    r.ox = __fmaf_rn(m0.z, oz, __fmaf_rn(m0.y, oy, __fmaf_rn(m0.x, ox, m0.w)));
+    r.oy = __fmaf_rn(m1.z, oz, __fmaf_rn(m1.y, oy, __fmaf_rn(m1.x, ox, m1.w)));
+    r.oz = __fmaf_rn(m2.z, oz, __fmaf_rn(m2.y, oy, __fmaf_rn(m2.x, ox, m2.w)));
+    r.dx = __fmaf_rn(m0.z, dz, __fmaf_rn(m0.y, dy, m0.x * dx));
+    r.dy = __fmaf_rn(m1.z, dz, __fmaf_rn(m1.y, dy, m1.x * dx));
+    r.dz = __fmaf_rn(m2.z, dz, __fmaf_rn(m2.y, dy, m2.x * dx));
+    r.finish();
+}
+
+/* Tests one triangle (a = v0|id, b = e1, c = e2) and updates the hit if (t, tri, inst) is lexicographically smaller. */
+template <bool MASKS>
+__device__ __forceinline__ bool tri_test(const TraceArgs& P, const float4 a, const float4 b, const float4 c, const RayRegs& r, float tmin, int cur_inst, HitRegs& h) {
+    float& tbest = h.tbest; float& ubest = h.ubest; int& tri_best = h.tri_best; int& inst_best = h.inst_best;
+    const int tri_id = __float_as_int(a.w);
+    // n = e1 x e2, unfused (what cpu_adapter.cpp:149 stores)
+    const float nx = b.y * c.z - b.z * c.y, ny = b.z * c.x - b.x * c.z, nz = b.x * c.y - b.y * c.x;
+    const float cx = a.x - r.ox, cy = a.y - r.oy, cz = a.z - r.oz;
+    const float rx = __fmaf_rn(r.dy, cz, -(r.dz * cy));
+    const float ry = __fmaf_rn(r.dz, cx, -(r.dx * cz));
+    const float rz = __fmaf_rn(r.dx, cy, -(r.dy * cx));
+    const float det = dot_f(nx, ny, nz, r.dx, r.dy, r.dz);
+    const float adet = fabsf(det);
+    const uint32_t sgn = __float_as_uint(det) & 0x80000000u;
+    const float U = xorf(dot_f(rx, ry, rz, c.x, c.y, c.z), sgn);
+    const float V = xorf(dot_f(rx, ry, rz, b.x, b.y, b.z), sgn);
+    if (!(U >= 0.0f) || !(V >= 0.0f) || !(U + V <= adet) || det == 0.0f) return false;
+    const float T = xorf(dot_f(nx, ny, nz, cx, cy, cz), sgn);
+    if (!(T >= adet * tmin) || !(T <= adet * tbest * IMBA_T_PREFILTER)) return false;
+    const float inv = 1.0f / adet;
+    const float t = T * inv, u = U * inv;
+    if (!(t < tbest || (t == tbest && (tri_id < tri_best || (tri_id == tri_best && cur_inst < inst_best))))) return false;
+    if (MASKS && !mask_opaque<MASKS>(P, tri_id, u, V * inv)) return false;
+    tbest = t; ubest = u; tri_best = tri_id; inst_best = cur_inst;
+    return true;
+}
+
+/* One ray, one thread, no work sharing: used where a handful of rays is traced inside another kernel.
+ * Same results as trace_kernel (same steps, same tie rule); returns true if something was hit (any hit: first found). */
+template <bool ANY, bool MASKS>
+__device__ __noinline__ bool trace_single(const TraceArgs& P, const float4 o, const float4 d, HitRegs& h) {
+    uint2 stack[IMBA_TRAVERSAL_STACK];
+    int sp = 0;
+    RayRegs r; r.ox = o.x; r.oy = o.y; r.oz = o.z; r.dx = d.x; r.dy = d.y; r.dz = d.z;
+    if (P.flat_inst >= 0) { r.ox += 0.0f; r.oy += 0.0f; r.oz += 0.0f; r.dx += 0.0f; r.dy += 0.0f; r.dz += 0.0f; }
+    r.finish();
+    const float tmin = o.w;
+    h.tbest = d.w; h.ubest = 0.0f; h.tri_best = IMBA_NO_HIT; h.inst_best = IMBA_NO_HIT;
+    int cur_inst = P.flat_inst;
+    uint2 ngroup = make_uint2(P.top_root, 0x80000000u), tgroup = make_uint2(0, 0);
+    for (;;) {
+        if (ngroup.y > 0x00ffffffu) {
+            const uint32_t hits = ngroup.y;
+            const uint32_t bit = 31u - (uint32_t)__clz(hits);
+            ngroup.y &= ~(1u << bit);
+            if (ngroup.y > 0x00ffffffu) stack[sp++] = ngroup;
+            const uint32_t slot = (bit - 24u) ^ (r.octinv4 & 0xffu);
+            const uint32_t rel = __popc(hits & 0xffu & ~(0xffffffffu << slot));
+            const uint4* np = P.nodes + (size_t)(ngroup.x + rel) * 5;
+            const uint4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
+            const uint32_t hitmask = node_step(n0, n1, n2, n3, n4, r, tmin, h.tbest);
+            ngroup = make_uint2(n1.x, (hitmask & 0xff000000u) | (n0.w >> 24));
+            tgroup = make_uint2(n1.y, hitmask & 0x00ffffffu);
+        } else { tgroup = ngroup; ngroup = make_uint2(0, 0); }
+        while (tgroup.y != 0) {
+            const uint32_t bit = 31u - (uint32_t)__clz(tgroup.y);
+            tgroup.y &= ~(1u << bit);
+            if (cur_inst < 0) {
+                if (ngroup.y > 0x00ffffffu) stack[sp++] = ngroup;
+                if (tgroup.y != 0) stack[sp++] = tgroup;
+                stack[sp++] = make_uint2(0xffffffffu, 0u);
+                const float4* ip = P.insts + (size_t)(tgroup.x + bit) * 4;
+                const float4 m0 = __ldg(ip), m1 = __ldg(ip + 1), m2 = __ldg(ip + 2);
+                const int4 id = __ldg((const int4*)(ip + 3));
+                enter_instance(r, m0, m1, m2);
+                cur_inst = id.x;
+                ngroup = make_uint2((uint32_t)id.y, 0x80000000u);
+                tgroup = make_uint2(0, 0);
+                break;
+            }
+            const float4* tp = P.tris + (size_t)(tgroup.x + bit) * 3;
+            if (tri_test<MASKS>(P, __ldg(tp), __ldg(tp + 1), __ldg(tp + 2), r, tmin, cur_inst, h) && ANY) return true;
+        }
+        if (ngroup.y <= 0x00ffffffu && tgroup.y == 0) {
+            for (;;) {
+                if (sp == 0) return h.tri_best != IMBA_NO_HIT;
+                const uint2 e = stack[--sp];
+                if (e.y == 0u) { r.ox = o.x; r.oy = o.y; r.oz = o.z; r.dx = d.x; r.dy = d.y; r.dz = d.z; r.finish(); cur_inst = -1; continue; }
+                ngroup = e;
+                break;
+            }
+        }
+    }
+}
+
+#endif

@@ -10,6 +10,7 @@
  * mis_pow(a) = powf(a, 1) = a (vcm.h:112-115) is applied as the identity.
  */
 #include "integrator.cuh"
+#include "traverse_core.cuh"
 #include "vcm.cuh"
 
 namespace {
@@ -86,23 +87,17 @@ __device__ __forceinline__ bool vcm_bounce(const VcmParams& P, VCMState& st, Rng
     return true;
 }
 
+/* One light-path vertex (process_light_rays, vcm.cpp:193-258): completes the MIS partials, appends to the vertex cache,
+ * builds the camera connection (shadow ray + contribution for the target pixel) and samples the next direction.
+ * Returns false when the path ends; otherwise (ro, rd, st) hold the continuation. */
 template <int ALGO>
-__global__ void __launch_bounds__(128) vcm_light_shade_kernel(const DeviceShading S, const VcmParams* Pd, const DevCamera cam, float4* rays, const int4* hits, VCMState* states,
-                                                              const int* sorted, const int* hit_count_ptr, const int* queue_count_ptr, float4* shadow_rays,
-                                                              ShadowState* shadow_states, DevLightVertex* cache, int cache_capacity, int* cache_last,
-                                                              unsigned long long* ray_stats, float4* out_rays, VCMState* out_states, int* out_count) {
-    const VcmParams P = *Pd;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i == 0 && ray_stats) atomicAdd(ray_stats, (unsigned long long)*queue_count_ptr);
-    if (i >= *hit_count_ptr) return;
-    const int idx = sorted[i];
-    const float4 ro = rays[2 * idx], rd = rays[2 * idx + 1];
-    const int4 h = hits[idx];
-    VCMState st = states[idx];
+__device__ __forceinline__ bool light_vertex(const DeviceShading& S, const VcmParams& P, const DevCamera& cam, float4& ro, float4& rd, const int4 h, VCMState& st,
+                                             DevLightVertex* cache, int cache_capacity, int* cache_last, bool& has_shadow, float4& sh_o, float4& sh_d, ShadowState& ss) {
+    has_shadow = false;
     const float t = __int_as_float(h.z);
     const Isect is = calc_intersection(S, ro, rd, h.x, h.y, t, __int_as_float(h.w));
     const float cos_theta_o = fabsf(dot(is.out_dir, is.normal));
-    if (cos_theta_o == 0.0f) { states[idx].pixel_id = -1; return; }
+    if (cos_theta_o == 0.0f) return false;
     const int path_length = (int)(st.len_finite & 0x7fffffffu);
     if (path_length > 1 || (st.len_finite >> 31)) st.dVCM *= sqr(t);
     st.dVCM *= 1.0f / cos_theta_o; st.dVC *= 1.0f / cos_theta_o; st.dVM *= 1.0f / cos_theta_o;
@@ -145,11 +140,10 @@ __global__ void __launch_bounds__(128) vcm_light_shade_kernel(const DeviceShadin
                         const float mis_weight = ALGO == IMBA_ALGO_LT ? 1.0f : (1.0f / (mis_weight_light + 1.0f));
                         const V3 c = thr * (mis_weight * bsdf_value * img_to_surf / (float)P.light_path_count);
                         const float off = dist * 1e-3f;
-                        shadow_rays[2 * idx] = make_float4(is.pos.x, is.pos.y, is.pos.z, off);
-                        shadow_rays[2 * idx + 1] = make_float4(dir_to_cam.x, dir_to_cam.y, dir_to_cam.z, dist - off);
-                        ShadowState ss; ss.pixel_id = pixel; ss.r = c.x; ss.g = c.y; ss.b = c.z;
-                        shadow_states[idx] = ss;
-                        if (ray_stats) atomicAdd(ray_stats + 1, 1ull);
+                        sh_o = make_float4(is.pos.x, is.pos.y, is.pos.z, off);
+                        sh_d = make_float4(dir_to_cam.x, dir_to_cam.y, dir_to_cam.z, dist - off);
+                        ss.pixel_id = pixel; ss.r = c.x; ss.g = c.y; ss.b = c.z;
+                        has_shadow = true;
                     }
                 }
             }
@@ -157,13 +151,66 @@ __global__ void __launch_bounds__(128) vcm_light_shade_kernel(const DeviceShadin
     }
     Rng rng; rng.s = st.rng;
     float4 no, nd;
-    if (vcm_bounce<ALGO>(P, st, rng, is, bsdf, true, t * 1e-4f, no, nd)) {
-        st.rng = rng.s;
+    if (!vcm_bounce<ALGO>(P, st, rng, is, bsdf, true, t * 1e-4f, no, nd)) return false;
+    st.rng = rng.s; ro = no; rd = nd;
+    return true;
+}
+
+template <int ALGO>
+__global__ void __launch_bounds__(128) vcm_light_shade_kernel(const DeviceShading S, const VcmParams* Pd, const DevCamera cam, float4* rays, const int4* hits, VCMState* states,
+                                                              const int* sorted, const int* hit_count_ptr, const int* queue_count_ptr, float4* shadow_rays,
+                                                              ShadowState* shadow_states, DevLightVertex* cache, int cache_capacity, int* cache_last,
+                                                              unsigned long long* ray_stats, float4* out_rays, VCMState* out_states, int* out_count) {
+    const VcmParams P = *Pd;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0 && ray_stats) atomicAdd(ray_stats, (unsigned long long)*queue_count_ptr);
+    if (i >= *hit_count_ptr) return;
+    const int idx = sorted[i];
+    float4 ro = rays[2 * idx], rd = rays[2 * idx + 1];
+    VCMState st = states[idx];
+    bool has_shadow; float4 sh_o, sh_d; ShadowState ss;
+    const bool alive = light_vertex<ALGO>(S, P, cam, ro, rd, hits[idx], st, cache, cache_capacity, cache_last, has_shadow, sh_o, sh_d, ss);
+    if (has_shadow) {
+        shadow_rays[2 * idx] = sh_o; shadow_rays[2 * idx + 1] = sh_d; shadow_states[idx] = ss;
+        if (ray_stats) atomicAdd(ray_stats + 1, 1ull);
+    }
+    if (alive) {
         const int o = out_count ? queue_push_slot(out_count) : idx;
         (out_count ? out_states : states)[o] = st;
         float4* dst = (out_count ? out_rays : rays) + 2 * (size_t)o;
-        dst[0] = no; dst[1] = nd;
+        dst[0] = ro; dst[1] = rd;
     } else states[idx].pixel_id = -1;
+}
+
+/* Tail of the light pass: one thread follows one light path through ALL its remaining bounces (closest-hit traversal,
+ * vertex processing, camera-connection shadow ray and splat inline).  Light paths are not length-capped (vcm.cpp:133-139);
+ * in scenes with glass a few thousand paths bounce hundreds to thousands of times, which as wavefronts costs one
+ * launch-bound round per bounce.  Results are those of the wavefront kernels (same functions, same RNG streams). */
+template <int ALGO, bool MASKS>
+__global__ void __launch_bounds__(64) vcm_light_tail_kernel(const DeviceShading S, const VcmParams* Pd, const DevCamera cam, const TraceArgs T, const float4* rays,
+                                                            const VCMState* states, const int* count_ptr, DevLightVertex* cache, int cache_capacity, int* cache_last,
+                                                            float* fb, unsigned long long* ray_stats, int max_bounces) {
+    const VcmParams P = *Pd;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= *count_ptr) return;
+    float4 ro = rays[2 * i], rd = rays[2 * i + 1];
+    VCMState st = states[i];
+    unsigned long long traced = 0, shadows = 0;
+    for (int bounce = 0; bounce < max_bounces; ++bounce) {
+        HitRegs hr;
+        ++traced;
+        if (!trace_single<false, MASKS>(T, ro, rd, hr)) break;
+        const int4 h = make_int4(hr.tri_best, hr.inst_best, __float_as_int(hr.tbest), __float_as_int(hr.ubest));
+        bool has_shadow; float4 sh_o, sh_d; ShadowState ss;
+        const bool alive = light_vertex<ALGO>(S, P, cam, ro, rd, h, st, cache, cache_capacity, cache_last, has_shadow, sh_o, sh_d, ss);
+        if (has_shadow) {
+            ++shadows;
+            HitRegs occ;
+            if (!trace_single<true, MASKS>(T, sh_o, sh_d, occ)) add_contribution(fb, ss.pixel_id, v3(ss.r, ss.g, ss.b));
+        }
+        if (!alive) break;
+    }
+    if (ray_stats) { atomicAdd(ray_stats, traced); atomicAdd(ray_stats + 1, shadows); }
 }
 
 /* ---- photon hash grid (rangesearch.h) ------------------------------------------------------------------------- */
@@ -493,6 +540,20 @@ cudaError_t imba_vcm_camera_shade(int algo, const VcmLaunch& a, cudaStream_t st)
         case IMBA_ALGO_VCM_PT: return camera_shade<IMBA_ALGO_VCM_PT>(a, st);
         default:               return camera_shade<IMBA_ALGO_VCM>(a, st);
     }
+}
+
+cudaError_t imba_vcm_light_tail(int algo, bool masks, const VcmLaunch& a, const TraceArgs& T, int capacity, cudaStream_t st) {
+    if (capacity <= 0) return cudaSuccess;
+    const int grid = (capacity + 63) / 64, max_bounces = 1 << 20;
+#define TAIL(A, M) vcm_light_tail_kernel<A, M><<<grid, 64, 0, st>>>(*a.S, a.P, a.cam, T, a.rays, a.states, a.queue_count_ptr, a.cache, a.cache_capacity, a.cache_last, a.fb, a.ray_stats, max_bounces)
+    switch (algo) {
+        case IMBA_ALGO_BPT: if (masks) TAIL(IMBA_ALGO_BPT, true); else TAIL(IMBA_ALGO_BPT, false); break;
+        case IMBA_ALGO_PPM: if (masks) TAIL(IMBA_ALGO_PPM, true); else TAIL(IMBA_ALGO_PPM, false); break;
+        case IMBA_ALGO_LT:  if (masks) TAIL(IMBA_ALGO_LT, true);  else TAIL(IMBA_ALGO_LT, false); break;
+        default:            if (masks) TAIL(IMBA_ALGO_VCM, true); else TAIL(IMBA_ALGO_VCM, false); break;
+    }
+#undef TAIL
+    return cudaGetLastError();
 }
 
 /* HashGrid::build on the vertex cache; `cells` has `table` + 1 ints, block_sums (table / 2048 + 1) ints */

@@ -28,6 +28,7 @@ cudaError_t imba_vcm_light_raygen(const DeviceShading& S, const VcmParams* P, ui
 cudaError_t imba_vcm_camera_raygen(const DevCamera& cam, const VcmParams* P, int spp, uint32_t seed_base, int count, float4* rays, VCMState* states, int* count_out, cudaStream_t st);
 cudaError_t imba_vcm_light_shade(int algo, const VcmLaunch& a, cudaStream_t st);
 cudaError_t imba_vcm_camera_shade(int algo, const VcmLaunch& a, cudaStream_t st);
+cudaError_t imba_vcm_light_tail(int algo, bool masks, const VcmLaunch& a, const TraceArgs& T, int capacity, cudaStream_t st);
 cudaError_t imba_grid_build(const DevLightVertex* cache, const int* cache_last, int cache_capacity, float radius, GridParams* grid, int* bbox, int* cells, unsigned table,
                             int* block_sums, DevPhoton* photons, bool build_cells, cudaStream_t st);
 #endif

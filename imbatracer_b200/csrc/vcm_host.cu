@@ -70,6 +70,7 @@ static int set_params(imba_integrator* it, const VcmParams& P) {
 }
 
 constexpr int TAIL_RAYS = 65536, TAIL_WAVES = 32;
+constexpr int TAIL_MEGA_PATHS = 8192;  // below this many live light paths the per-path tail kernel takes over
 
 /* Light paths have no length cap (vcm.cpp:133-139): in scenes with glass a few paths bounce hundreds of times.  Once the
  * queue is small the wavefront is launch-bound, so TAIL_WAVES wavefronts (sized for TAIL_RAYS rays, counts in device
@@ -100,7 +101,15 @@ static int light_pass(imba_integrator* it, int algo, uint32_t seed_base, int pat
     // The queue size is read back only every `batch` wavefronts (the grid stays sized for the last known count; kernels on
     // an already empty queue return at once), so long light paths do not cost one host round trip per bounce.
     int cur = 0, n = path_count, w = 0, batch = 2;
+    const int mega = getenv("IMBA_TAIL_PATHS") ? atoi(getenv("IMBA_TAIL_PATHS")) : TAIL_MEGA_PATHS;
     while (n > 0) {
+        if (use_graph && n <= mega) { // few paths left: one thread per path follows it to its end (vcm.cu: vcm_light_tail_kernel)
+            TraceArgs T; imba_scene_trace_args(it->scene, &T);
+            const VcmLaunch a = base_launch(it, cur, n);
+            IMBA_CUDA(imba_vcm_light_tail(algo, it->scene->has_masks, a, T, n, it->stream), IMBA_ERR_CUDA);
+            g_imba_launches.fetch_add(1); ++w;
+            break;
+        }
         const int tail_rays = std::min(TAIL_RAYS, it->capacity);
         if (use_graph && n <= tail_rays && cur == 0) {
             if (!it->tail_graph) { const int rc = build_tail_graph(it, algo); if (rc != IMBA_OK) return rc; }
