@@ -87,6 +87,12 @@ NODE8 = np.dtype([("p", "<f4", 3), ("e", "u1", 3), ("imask", "u1"), ("child_base
                   ("meta", "u1", 8), ("q", "u1", (6, 8))])
 PT_STATE = np.dtype([("pixel_id", "<i4"), ("sample_id", "<i4"), ("rng", "<u8"), ("throughput", "<f4", 3), ("bounces_spec", "<u4"),
                      ("last_pdf", "<f4"), ("pad", "<u4")])
+VCM_STATE = np.dtype([("pixel_id", "<i4"), ("light_id", "<i4"), ("rng", "<u8"), ("throughput", "<f4", 3), ("len_finite", "<u4"),
+                      ("dVC", "<f4"), ("dVCM", "<f4"), ("dVM", "<f4"), ("pad", "<u4")])
+LIGHT_VERTEX = np.dtype([("pos", "<f4", 3), ("path_length", "<i4"), ("out_dir", "<f4", 3), ("mat", "<i4"), ("normal", "<f4", 3), ("dVC", "<f4"),
+                         ("geom_normal", "<f4", 3), ("dVCM", "<f4"), ("u_tangent", "<f4", 3), ("dVM", "<f4"), ("v_tangent", "<f4", 3), ("uv_x", "<f4"),
+                         ("throughput", "<f4", 3), ("uv_y", "<f4")])
+assert VCM_STATE.itemsize == 48 and LIGHT_VERTEX.itemsize == 112
 SHADOW_STATE = np.dtype([("pixel_id", "<i4"), ("throughput", "<f4", 3)])
 assert PT_STATE.itemsize == 40 and SHADOW_STATE.itemsize == 16
 TRI48 = np.dtype([("v0", "<f4", 3), ("id", "<i4"), ("e1", "<f4", 3), ("pad0", "<f4"), ("e2", "<f4", 3), ("pad1", "<f4")])
@@ -142,6 +148,8 @@ def lib():
     L.imba_integrator_camera_rays.argtypes = [vp, i32, vp, vp]
     L.imba_seed_states.argtypes = [u32, i32, i32, i32, vp]
     L.imba_pt_shade_batch.argtypes = [vp, i32] + [vp] * 9
+    L.imba_vcm_stage_batch.argtypes = [vp, i32, i32, f32, i32, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.imba_vcm_raygen_batch.argtypes = [vp, i32, i32, f32, u32, i32, vp, vp]
     L.imba_queue_sort_by_material.argtypes = [vp, vp, i32, vp, vp, vp]
     L.imba_queue_compact_rays.argtypes = [vp, vp, i32, vp, vp, i32, vp, vp]
     L.imba_queue_compact_hits.argtypes = [vp, vp, vp, vp, i32, vp, vp, vp, i32, vp, vp]

@@ -146,3 +146,21 @@ class Integrator:
                                              states_out.ctypes.data, C.addressof(nc), sh_rays.ctypes.data, sh_states.ctypes.data, C.addressof(ns)),
                   "imba_pt_shade_batch")
         return rays_out[:nc.value], states_out[:nc.value], sh_rays[:ns.value], sh_states[:ns.value]
+
+    def vcm_raygen_batch(self, light, iteration, base_radius, seed_base, count):
+        rays = np.zeros(count, abi.RAY); states = np.zeros(count, abi.VCM_STATE)
+        abi.check(self.L.imba_vcm_raygen_batch(self.h, int(light), iteration, base_radius, seed_base, count, rays.ctypes.data, states.ctypes.data), "imba_vcm_raygen_batch")
+        return rays, states
+
+    def vcm_stage_batch(self, stage, iteration, base_radius, rays, hits, states, cache_in=None):
+        n = len(rays); slots = self.settings.num_connections + 1
+        assert rays.dtype == abi.RAY and hits.dtype == abi.HIT and states.dtype == abi.VCM_STATE
+        rays_out = np.zeros(n, abi.RAY); states_out = np.zeros(n, abi.VCM_STATE)
+        sh_rays = np.zeros(n * slots, abi.RAY); sh_states = np.zeros(n * slots, abi.SHADOW_STATE)
+        cache_out = np.zeros(2 * n + 16, abi.LIGHT_VERTEX)
+        nc, ns, nv = C.c_int(), C.c_int(), C.c_int()
+        cin = np.ascontiguousarray(cache_in) if cache_in is not None else np.zeros(0, abi.LIGHT_VERTEX)
+        abi.check(self.L.imba_vcm_stage_batch(self.h, stage, iteration, base_radius, n, rays.ctypes.data, hits.ctypes.data, states.ctypes.data,
+                                              cin.ctypes.data if len(cin) else None, len(cin), rays_out.ctypes.data, states_out.ctypes.data, C.addressof(nc),
+                                              sh_rays.ctypes.data, sh_states.ctypes.data, C.addressof(ns), cache_out.ctypes.data, C.addressof(nv)), "imba_vcm_stage_batch")
+        return rays_out[:nc.value], states_out[:nc.value], sh_rays[:ns.value], sh_states[:ns.value], cache_out[:nv.value]

@@ -70,7 +70,7 @@ static int set_params(imba_integrator* it, const VcmParams& P) {
 }
 
 constexpr int TAIL_RAYS = 65536, TAIL_WAVES = 32;
-constexpr int TAIL_MEGA_PATHS = 8192;  // below this many live light paths the per-path tail kernel takes over
+constexpr int TAIL_MEGA_PATHS = 131072;  // below this many live light paths the per-path tail kernel takes over
 
 /* Light paths have no length cap (vcm.cpp:133-139): in scenes with glass a few paths bounce hundreds of times.  Once the
  * queue is small the wavefront is launch-bound, so TAIL_WAVES wavefronts (sized for TAIL_RAYS rays, counts in device
@@ -218,5 +218,107 @@ int imba_vcm_render_iteration(imba_integrator* it) {
             if (rc != IMBA_OK) return rc;
         }
     }
+    return IMBA_OK;
+}
+
+/* ---- parity harness: one VCM stage on an injected batch -----------------------------------------------------------------
+ * stage 0 = process_light_rays (vcm.cpp:193-258), stage 1 = process_camera_rays (vcm.cpp:323-439) for the integrator's
+ * algorithm at progressive iteration `iteration` (1-based, as cur_iteration_ after the increment in render()).
+ * Host pointers, synchronous.  Light stage: the vertex cache is cleared first and returned (112-byte DevLightVertex
+ * records, append order).  Camera stage: `h_cache_in` is installed as the vertex cache (and the photon grid is built on
+ * it for PPM / VCM) before shading.  Outputs like imba_pt_shade_batch: continuation queue (stable order), shadow queue
+ * (slot order, empty slots removed); contributions go to the accumulation buffer. */
+extern "C" int imba_vcm_stage_batch(imba_integrator* it, int stage, int iteration, float base_radius, int count, const imba_ray* h_rays,
+                                    const imba_hit* h_hits, const void* h_states, const void* h_cache_in, int cache_in_count,
+                                    imba_ray* h_rays_out, void* h_states_out, int* out_count, imba_ray* h_shadow_rays, void* h_shadow_states,
+                                    int* shadow_count, void* h_cache_out, int* cache_out_count) {
+    if (!it || it->cfg.algorithm == IMBA_ALGO_PT || !it->cache_last || count < 0 || count > it->capacity || iteration < 1) {
+        imba_set_error("needs a preprocessed VCM-family integrator whose queue capacity covers the batch"); return IMBA_ERR_INVALID;
+    }
+    const int algo = it->cfg.algorithm;
+    const DeviceShading& S = *imba_shading_view(it->scene);
+    cudaStream_t st = it->stream;
+    it->base_radius = base_radius;
+    const VcmParams P = iteration_params(it, (uint64_t)iteration);
+    int rc = set_params(it, P);
+    if (rc != IMBA_OK) return rc;
+    const int slots = stage == 0 ? 1 : it->shadow_slots;
+    IMBA_CUDA(cudaMemcpyAsync(it->rays[0], h_rays, (size_t)count * 32, cudaMemcpyHostToDevice, st), IMBA_ERR_CUDA);
+    IMBA_CUDA(cudaMemcpyAsync(it->hits, h_hits, (size_t)count * 16, cudaMemcpyHostToDevice, st), IMBA_ERR_CUDA);
+    IMBA_CUDA(cudaMemcpyAsync(it->states[0], h_states, (size_t)count * sizeof(VCMState), cudaMemcpyHostToDevice, st), IMBA_ERR_CUDA);
+    IMBA_CUDA(cudaMemcpyAsync(it->count[0], &count, 4, cudaMemcpyHostToDevice, st), IMBA_ERR_CUDA);
+    if (stage == 0) {
+        IMBA_CUDA(cudaMemsetAsync(it->cache_last, 0, sizeof(int), st), IMBA_ERR_CUDA);
+    } else {
+        if (cache_in_count > it->cache_capacity) { imba_set_error("vertex cache too small for the injected vertices"); return IMBA_ERR_OVERFLOW; }
+        IMBA_CUDA(cudaMemcpyAsync(it->cache, h_cache_in, (size_t)cache_in_count * sizeof(DevLightVertex), cudaMemcpyHostToDevice, st), IMBA_ERR_CUDA);
+        IMBA_CUDA(cudaMemcpyAsync(it->cache_last, &cache_in_count, 4, cudaMemcpyHostToDevice, st), IMBA_ERR_CUDA);
+        IMBA_CUDA(cudaStreamSynchronize(st), IMBA_ERR_CUDA);
+        IMBA_CUDA(imba_grid_build(it->cache, it->cache_last, it->cache_capacity, P.pm_radius, it->grid, it->grid_bbox, it->cells, it->table, it->block_sums,
+                                  it->photons, algo != IMBA_ALGO_BPT && algo != IMBA_ALGO_VCM_PT, st), IMBA_ERR_CUDA);
+    }
+    IMBA_CUDA(imba_sort_hits_by_material(it->part, it->hits, S.indices, S.material_count, (int*)it->shadow_states, slots, it->count[0], 0, count, st), IMBA_ERR_CUDA);
+    VcmLaunch a = base_launch(it, 0, count);
+    a.out_rays = nullptr; a.out_states = nullptr; a.out_count = nullptr; // continuation in place, then the stable compaction
+    IMBA_CUDA(stage == 0 ? imba_vcm_light_shade(algo, a, st) : imba_vcm_camera_shade(algo, a, st), IMBA_ERR_CUDA);
+    // shadow queue: valid slots compacted into rays[1] / states[1]
+    int n = 0;
+    const int nslots = count * slots;
+    if (nslots > it->capacity * it->shadow_slots) { imba_set_error("shadow queue too small"); return IMBA_ERR_OVERFLOW; }
+    {   // the partition buffers cover `capacity` entries: compact the shadow slots in pieces of at most `capacity`
+        int done = 0, total = 0;
+        while (done < nslots) {
+            const int piece = std::min(it->capacity, nslots - done);
+            IMBA_CUDA(imba_compact_alive(it->part, nullptr, it->shadow_rays + 2 * (size_t)done, it->shadow_states + done, sizeof(ShadowState), nullptr, piece, piece,
+                                         it->rays[1], it->states[1], it->count[1], st), IMBA_ERR_CUDA);
+            IMBA_CUDA(cudaMemcpyAsync(&n, it->count[1], 4, cudaMemcpyDeviceToHost, st), IMBA_ERR_CUDA);
+            IMBA_CUDA(cudaStreamSynchronize(st), IMBA_ERR_CUDA);
+            if (piece == 0) n = 0;
+            IMBA_CUDA(cudaMemcpyAsync(h_shadow_rays + total, it->rays[1], (size_t)n * 32, cudaMemcpyDeviceToHost, st), IMBA_ERR_CUDA);
+            IMBA_CUDA(cudaMemcpyAsync((char*)h_shadow_states + (size_t)total * sizeof(ShadowState), it->states[1], (size_t)n * sizeof(ShadowState), cudaMemcpyDeviceToHost, st), IMBA_ERR_CUDA);
+            IMBA_CUDA(cudaStreamSynchronize(st), IMBA_ERR_CUDA);
+            total += n; done += piece;
+            if (piece == 0) break;
+        }
+        *shadow_count = total;
+    }
+    IMBA_CUDA(imba_compact_alive(it->part, it->hits, it->rays[0], it->states[0], sizeof(VCMState), it->count[0], 0, count,
+                                 it->rays[1], it->states[1], it->count[1], st), IMBA_ERR_CUDA);
+    IMBA_CUDA(cudaMemcpyAsync(&n, it->count[1], 4, cudaMemcpyDeviceToHost, st), IMBA_ERR_CUDA);
+    IMBA_CUDA(cudaStreamSynchronize(st), IMBA_ERR_CUDA);
+    if (count == 0) n = 0;
+    IMBA_CUDA(cudaMemcpyAsync(h_rays_out, it->rays[1], (size_t)n * 32, cudaMemcpyDeviceToHost, st), IMBA_ERR_CUDA);
+    IMBA_CUDA(cudaMemcpyAsync(h_states_out, it->states[1], (size_t)n * sizeof(VCMState), cudaMemcpyDeviceToHost, st), IMBA_ERR_CUDA);
+    *out_count = n;
+    int nv = 0;
+    if (stage == 0 && h_cache_out) {
+        IMBA_CUDA(cudaMemcpyAsync(&nv, it->cache_last, 4, cudaMemcpyDeviceToHost, st), IMBA_ERR_CUDA);
+        IMBA_CUDA(cudaStreamSynchronize(st), IMBA_ERR_CUDA);
+        nv = std::min(nv, it->cache_capacity);
+        IMBA_CUDA(cudaMemcpyAsync(h_cache_out, it->cache, (size_t)nv * sizeof(DevLightVertex), cudaMemcpyDeviceToHost, st), IMBA_ERR_CUDA);
+    }
+    if (cache_out_count) *cache_out_count = nv;
+    IMBA_CUDA(cudaStreamSynchronize(st), IMBA_ERR_CUDA);
+    g_imba_launches.fetch_add(12);
+    return IMBA_OK;
+}
+
+/* Parity harness: the rays and 48-byte states the light (light = 1) or camera (light = 0) ray generation produces for
+ * `count` paths / samples with the given seed base and iteration constants (vcm.cpp:64-96, 109-129). */
+extern "C" int imba_vcm_raygen_batch(imba_integrator* it, int light, int iteration, float base_radius, uint32_t seed_base, int count, imba_ray* h_rays, void* h_states) {
+    if (!it || it->cfg.algorithm == IMBA_ALGO_PT || !it->d_params || count < 0 || count > it->capacity || iteration < 1) {
+        imba_set_error("needs a preprocessed VCM-family integrator whose queue capacity covers the batch"); return IMBA_ERR_INVALID;
+    }
+    it->base_radius = base_radius;
+    const VcmParams P = iteration_params(it, (uint64_t)iteration);
+    int rc = set_params(it, P);
+    if (rc != IMBA_OK) return rc;
+    const DeviceShading& S = *imba_shading_view(it->scene);
+    if (light) IMBA_CUDA(imba_vcm_light_raygen(S, it->d_params, seed_base, count, it->rays[0], (VCMState*)it->states[0], it->count[0], it->stream), IMBA_ERR_CUDA);
+    else       IMBA_CUDA(imba_vcm_camera_raygen(it->cam, it->d_params, it->cfg.spp, seed_base, count, it->rays[0], (VCMState*)it->states[0], it->count[0], it->stream), IMBA_ERR_CUDA);
+    IMBA_CUDA(cudaMemcpyAsync(h_rays, it->rays[0], (size_t)count * 32, cudaMemcpyDeviceToHost, it->stream), IMBA_ERR_CUDA);
+    IMBA_CUDA(cudaMemcpyAsync(h_states, it->states[0], (size_t)count * sizeof(VCMState), cudaMemcpyDeviceToHost, it->stream), IMBA_ERR_CUDA);
+    IMBA_CUDA(cudaStreamSynchronize(it->stream), IMBA_ERR_CUDA);
+    g_imba_launches.fetch_add(1);
     return IMBA_OK;
 }

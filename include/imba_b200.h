@@ -297,6 +297,20 @@ int   imba_integrator_ray_counts(imba_integrator* it, uint64_t out[2]);
 int imba_integrator_camera_rays(imba_integrator* it, int count, const float* raster_xy, imba_ray* h_rays);
 int imba_seed_states(uint32_t seed_base, int first, int count, int spp, uint64_t* out);
 
+/* One VCM stage on an injected batch (parity harness for vcm.cpp:193-258 and 323-439, light_vertices.h:77-84,
+ * rangesearch.h:25-129).  stage 0 = process_light_rays: returns continuation queue, camera-connection shadow queue and
+ * the vertex cache (112-byte records: pos|path_length, out_dir|material, normal|dVC, geom_normal|dVCM, u_tangent|dVM,
+ * v_tangent|uv.x, throughput|uv.y).  stage 1 = process_camera_rays with `h_cache_in` installed as the vertex cache (photon
+ * grid rebuilt for PPM / VCM).  States are the reference's 48-byte VCMState; `iteration` is 1-based.  Host pointers. */
+int imba_vcm_stage_batch(imba_integrator* it, int stage, int iteration, float base_radius, int count, const imba_ray* h_rays,
+                         const imba_hit* h_hits, const void* h_states, const void* h_cache_in, int cache_in_count,
+                         imba_ray* h_rays_out, void* h_states_out, int* out_count, imba_ray* h_shadow_rays, void* h_shadow_states,
+                         int* shadow_count, void* h_cache_out, int* cache_out_count);
+
+/* Rays and 48-byte states produced by the light (light = 1) or camera (0) ray generation of a VCM-family integrator. */
+int imba_vcm_raygen_batch(imba_integrator* it, int light, int iteration, float base_radius, uint32_t seed_base, int count, imba_ray* h_rays,
+                          void* h_states);
+
 int imba_pt_shade_batch(imba_integrator* it, int count, const imba_ray* h_rays, const imba_hit* h_hits,
                         const void* h_states, imba_ray* h_rays_out, void* h_states_out, int* out_count,
                         imba_ray* h_shadow_rays, void* h_shadow_states, int* shadow_count);

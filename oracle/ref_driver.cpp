@@ -123,6 +123,67 @@ public:
 
 } // namespace
 
+namespace {
+struct ExportVertex { float pos[3]; int path_length; float out_dir[3]; int mat; float normal[3]; float dVC; float geom_normal[3]; float dVCM;
+                      float u_tangent[3]; float dVM; float v_tangent[3]; float uv_x; float throughput[3]; float uv_y; };
+static_assert(sizeof(ExportVertex) == 112, "vertex export record");
+
+template <typename Integ>
+int run_vcm_stage(Scene& scene, PerspectiveCamera& cam, const UserSettings& s, float base_radius, int iteration, int stage, int count, const imba_ray* rays,
+                  const imba_hit* hits, const void* states, const ExportVertex* cache_in, int cache_in_count, imba_ray* rays_out, void* states_out, int* out_count,
+                  imba_ray* shadow_rays, void* shadow_states, int* shadow_count, float* fb_rgb, ExportVertex* cache_out, int* cache_out_count) {
+    static_assert(sizeof(VCMState) == 48 && sizeof(VCMShadowState) == 16, "state sizes");
+    BatchScheduler<VCMState, VCMShadowState> sched(scene);
+    Integ integ(scene, cam, sched, s);
+    // what VCMIntegrator::preprocess / render would have set (vcm.h:74-81, vcm.cpp:28-46)
+    const float radius_alpha = 0.75f;
+    integ.base_radius_ = base_radius;
+    integ.cur_iteration_ = iteration;
+    integ.pm_radius_ = std::max(base_radius / powf(static_cast<float>(iteration), 0.5f * (1.0f - radius_alpha)), 1e-7f);
+    const float eta_vcm = pi * sqr(integ.pm_radius_) * s.light_path_count;
+    integ.mis_eta_vc_ = 1.0f / eta_vcm;
+    integ.mis_eta_vm_ = std::is_same<Integ, BPT>::value ? 0.0f : eta_vcm;
+    auto& lv = integ.light_vertices_;
+    const int cache_size = std::max(count * 2, cache_in_count) + 16;
+    lv.cache_.resize(cache_size); lv.last_.store(0); lv.count_ = 0;
+    RayQueue<VCMState> prim(count, false); RayQueue<VCMShadowState> shadow(count * (s.num_connections + 1), false);
+    const VCMState* st = (const VCMState*)states;
+    for (int i = 0; i < count; ++i) { ::Ray r; memcpy(&r, &rays[i], 32); prim.push(r, st[i]); }
+    memcpy(prim.hits(), hits, sizeof(Hit) * count);
+    AtomicImage img(s.width, s.height); img.clear();
+    if (stage == 0) {
+        integ.process_light_rays(prim, shadow, img);
+        const int n = std::min<int>(lv.cache_.size(), lv.last_.load());
+        for (int i = 0; i < n; ++i) {
+            const LightPathVertex& v = lv.cache_[i]; ExportVertex& o = cache_out[i];
+            for (int k = 0; k < 3; ++k) { o.pos[k] = v.isect.pos[k]; o.out_dir[k] = v.isect.out_dir[k]; o.normal[k] = v.isect.normal[k]; o.geom_normal[k] = v.isect.geom_normal[k];
+                                          o.u_tangent[k] = v.isect.u_tangent[k]; o.v_tangent[k] = v.isect.v_tangent[k]; o.throughput[k] = v.throughput[k]; }
+            o.path_length = v.path_length; o.dVC = v.dVC; o.dVCM = v.dVCM; o.dVM = v.dVM; o.uv_x = v.isect.uv.x; o.uv_y = v.isect.uv.y;
+            o.mat = -1; for (size_t m = 0; m < scene.material_count(); ++m) if (scene.material(m).get() == v.isect.mat) { o.mat = (int)m; break; }
+        }
+        *cache_out_count = n;
+    } else {
+        for (int i = 0; i < cache_in_count; ++i) {
+            const ExportVertex& o = cache_in[i]; LightPathVertex v;
+            for (int k = 0; k < 3; ++k) { v.isect.pos[k] = o.pos[k]; v.isect.out_dir[k] = o.out_dir[k]; v.isect.normal[k] = o.normal[k]; v.isect.geom_normal[k] = o.geom_normal[k];
+                                          v.isect.u_tangent[k] = o.u_tangent[k]; v.isect.v_tangent[k] = o.v_tangent[k]; v.throughput[k] = o.throughput[k]; }
+            v.isect.uv.x = o.uv_x; v.isect.uv.y = o.uv_y; v.isect.mat = scene.material(o.mat).get();
+            v.path_length = o.path_length; v.dVC = o.dVC; v.dVCM = o.dVCM; v.dVM = o.dVM;
+            lv.cache_[i] = v;
+        }
+        lv.last_.store(cache_in_count);
+        lv.build(integ.pm_radius_, !std::is_same<Integ, BPT>::value && !std::is_same<Integ, VCM_PT>::value);
+        integ.process_camera_rays(prim, shadow, img);
+        if (cache_out_count) *cache_out_count = 0;
+    }
+    *out_count = prim.size(); *shadow_count = shadow.size();
+    memcpy(rays_out, prim.rays(), 32 * prim.size()); memcpy(states_out, prim.states(), sizeof(VCMState) * prim.size());
+    memcpy(shadow_rays, shadow.rays(), 32 * shadow.size()); memcpy(shadow_states, shadow.states(), sizeof(VCMShadowState) * shadow.size());
+    if (fb_rgb) for (int i = 0; i < s.width * s.height; ++i) { fb_rgb[3 * i] = img.pixels()[i][0]; fb_rgb[3 * i + 1] = img.pixels()[i][1]; fb_rgb[3 * i + 2] = img.pixels()[i][2]; }
+    return 0;
+}
+} // namespace
+
 extern "C" {
 
 void* ref_scene_load(const char* path, int gpu_layout) {
@@ -363,6 +424,29 @@ int ref_pt_shade_batch(void* h, int w, int hgt, float fov, int max_path_len, int
     memcpy(shadow_rays, shadow.rays(), 32 * shadow.size()); memcpy(shadow_states, shadow.states(), sizeof(ShadowState) * shadow.size());
     if (fb_rgb) for (int i = 0; i < w * hgt; ++i) { fb_rgb[3 * i] = img.pixels()[i][0]; fb_rgb[3 * i + 1] = img.pixels()[i][1]; fb_rgb[3 * i + 2] = img.pixels()[i][2]; }
     return 0;
+}
+
+/// VCMIntegrator<algo>::process_light_rays (stage 0, vcm.cpp:193-258) or process_camera_rays (stage 1, vcm.cpp:323-439) of
+/// the unmodified reference on an injected batch, with the iteration constants render() would have set.
+int ref_vcm_stage(void* h, int algo, int w, int hgt, float fov, int max_path_len, int light_path_count, int num_connections, int num_knn, float base_radius,
+                  int iteration, int stage, int count, const imba_ray* rays, const imba_hit* hits, const void* states, const void* cache_in, int cache_in_count,
+                  imba_ray* rays_out, void* states_out, int* out_count, imba_ray* shadow_rays, void* shadow_states, int* shadow_count, float* fb_rgb,
+                  void* cache_out, int* cache_out_count) {
+    Quiet q;
+    auto rs = (RefScene*)h; Scene& scene = *rs->scene;
+    UserSettings s;
+    s.width = w; s.height = hgt; s.fov = fov; s.concurrent_spp = 1; s.thread_count = 1; s.tile_size = 64; s.max_path_len = max_path_len;
+    s.light_path_count = light_path_count; s.num_connections = num_connections; s.num_knn = num_knn; s.radius_factor = 2.0f;
+    s.traversal_platform = UserSettings::cpu; s.algorithm = (UserSettings::Algorithm)algo;
+    PerspectiveCamera cam(w, hgt, fov);
+    setup_camera(cam, rs->cam_pos, rs->cam_dir, rs->cam_up);
+#define STAGE(T) return run_vcm_stage<T>(scene, cam, s, base_radius, iteration, stage, count, rays, hits, states, (const ExportVertex*)cache_in, cache_in_count, rays_out, \
+                                         states_out, out_count, shadow_rays, shadow_states, shadow_count, fb_rgb, (ExportVertex*)cache_out, cache_out_count)
+    switch (s.algorithm) {
+        case UserSettings::BPT: STAGE(BPT); case UserSettings::PPM: STAGE(PPM); case UserSettings::LT: STAGE(LT);
+        case UserSettings::VCM_PT: STAGE(VCM_PT); default: STAGE(VCM);
+    }
+#undef STAGE
 }
 
 /// calculate_intersection (integrator.h:71-123) on a batch; out: 20 floats per hit

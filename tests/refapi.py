@@ -62,6 +62,7 @@ def ref():
         L.ref_seed_states.restype = None; L.ref_seed_states.argtypes = [C.c_uint64, i32, i32, i32, vp]
         L.ref_struct_sizes.argtypes = [vp]
         L.ref_scene_add_test_textures.argtypes = [vp, C.c_uint64]
+        L.ref_vcm_stage.argtypes = [vp, i32, i32, i32, f32, i32, i32, i32, i32, f32, i32, i32, i32, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp]
         _ref = L
     return _ref
 
@@ -181,3 +182,19 @@ class RefScene:
                                        sh_states.ctypes.data, C.addressof(ns), fb.ctypes.data)
         assert rc == 0
         return rays_out[:nc.value], states_out[:nc.value], sh_rays[:ns.value], sh_states[:ns.value], fb
+
+    def vcm_stage(self, algo, w, h, stage, iteration, base_radius, rays, hits, states, cache_in=None, light_path_count=0, max_path_len=10,
+                  num_connections=1, num_knn=10, fov=60.0):
+        """VCMIntegrator<algo>::process_light_rays (stage 0) / process_camera_rays (stage 1) of the reference on a batch."""
+        n = len(rays); slots = num_connections + 1
+        rays_out = np.zeros(n, abi.RAY); states_out = np.zeros(n, abi.VCM_STATE)
+        sh_rays = np.zeros(n * slots, abi.RAY); sh_states = np.zeros(n * slots, abi.SHADOW_STATE)
+        fb = np.zeros((h, w, 3), np.float32); cache_out = np.zeros(2 * n + 16, abi.LIGHT_VERTEX)
+        nc, ns, nv = C.c_int(), C.c_int(), C.c_int()
+        cin = np.ascontiguousarray(cache_in) if cache_in is not None else np.zeros(0, abi.LIGHT_VERTEX)
+        rc = self.L.ref_vcm_stage(self.h, algo, w, h, fov, max_path_len, light_path_count or w * h // 2, num_connections, num_knn, base_radius, iteration, stage, n,
+                                  rays.ctypes.data, hits.ctypes.data, states.ctypes.data, cin.ctypes.data if len(cin) else None, len(cin),
+                                  rays_out.ctypes.data, states_out.ctypes.data, C.addressof(nc), sh_rays.ctypes.data, sh_states.ctypes.data, C.addressof(ns),
+                                  fb.ctypes.data, cache_out.ctypes.data, C.addressof(nv))
+        assert rc == 0
+        return rays_out[:nc.value], states_out[:nc.value], sh_rays[:ns.value], sh_states[:ns.value], fb, cache_out[:nv.value]
