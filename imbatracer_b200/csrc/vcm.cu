@@ -237,6 +237,11 @@ __global__ void grid_prepare_kernel(const int* bbox, const int* last, int capaci
     for (int a = 0; a < 3; ++a) { const float e = hi[a] - lo[a]; hi[a] += e * 0.001f; lo[a] -= e * 0.001f; }
     g->lo[0] = lo[0]; g->lo[1] = lo[1]; g->lo[2] = lo[2]; g->hi[0] = hi[0]; g->hi[1] = hi[1]; g->hi[2] = hi[2];
     g->radius_sqr = radius * radius; g->inv_cell_size = 1.f / (radius * 2.f); g->count = n;
+    // the reference's table has 2 * photon_count cells and is only re-allocated when it must grow; the size matters for
+    // results, not just speed: two of the 8 query cells that collide make their photons count twice (rangesearch.h:96-127)
+    const unsigned want = (unsigned)n * 2u;
+    if (g->table < want) g->table = want;
+    if (g->table == 0) g->table = 1;
 }
 
 __device__ __forceinline__ unsigned cell_hash(unsigned x, unsigned y, unsigned z, unsigned table) {
@@ -247,8 +252,8 @@ __device__ __forceinline__ unsigned cell_of(const GridParams& g, V3 p, unsigned 
     return cell_hash((unsigned)cx, (unsigned)cy, (unsigned)cz, table);
 }
 
-__global__ void grid_count_kernel(const DevLightVertex* cache, const GridParams* gp, int* cells, unsigned table) {
-    const GridParams g = *gp;
+__global__ void grid_count_kernel(const DevLightVertex* cache, const GridParams* gp, int* cells, unsigned) {
+    const GridParams g = *gp; const unsigned table = g.table;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= g.count) return;
     atomicAdd(cells + cell_of(g, v3(cache[i].pos_len), table), 1);
@@ -305,8 +310,8 @@ __global__ void scan_add_kernel(int* data, int n, const int* block_sums) {
     if (i < n) data[i] += block_sums[i / SCAN_CHUNK];
 }
 
-__global__ void grid_scatter_kernel(const DevLightVertex* cache, const GridParams* gp, int* cells, unsigned table, DevPhoton* photons) {
-    const GridParams g = *gp;
+__global__ void grid_scatter_kernel(const DevLightVertex* cache, const GridParams* gp, int* cells, unsigned, DevPhoton* photons) {
+    const GridParams g = *gp; const unsigned table = g.table;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= g.count) return;
     const DevLightVertex v = cache[i];
@@ -471,7 +476,7 @@ __global__ void __launch_bounds__(128) vcm_camera_shade_kernel(const DeviceShadi
     if (ALGO != IMBA_ALGO_BPT && ALGO != IMBA_ALGO_VCM_PT && !bsdf.is_specular()) { // vertex_merging (vcm.cpp:572-611)
         int found[IMBA_MAX_KNN]; float dist[IMBA_MAX_KNN];
         const int k = P.num_knn;
-        const int count = grid_query(g, cells, table, photons, is.pos, k, found, dist);
+        const int count = grid_query(g, cells, g.table, photons, is.pos, k, found, dist);
         const float radius_sqr = (count == k) ? dist[k - 1] : (P.pm_radius * P.pm_radius);
         V3 contrib = v3(0.0f);
         for (int j = 0; j < count; ++j) {

@@ -13,6 +13,7 @@ struct GridParams {           // HashGrid members (rangesearch.h:148-156) + the 
     float lo[3], hi[3];
     float radius_sqr, inv_cell_size;
     int   count;
+    unsigned table;           // cell_ends_.size(): 2 * photon count, only ever grows (rangesearch.h:26,34-35)
 };
 struct VcmLaunch {
     const DeviceShading* S; const VcmParams* P; DevCamera cam;   // P lives in device memory: launches (and captured graphs) stay valid across iterations

@@ -76,3 +76,42 @@ def test_vcm_needs_preprocess_and_valid_settings():
     with pytest.raises(RuntimeError, match="knn"):
         api.Integrator(sc, api.render_settings(flat, "vcm", 32, 32, num_knn=64))
     sc.close()
+
+
+@needs_ref
+@pytest.mark.parametrize("scene", ["cornell_org", "cornell_specular_front", "cornell_instances"])
+@pytest.mark.parametrize("algo", ["vcm", "bpt", "ppm", "lt", "vcm_pt"])
+def test_vcm_stages_match_reference_wavefronts(scene, algo):
+    """Stage level: the reference's own process_light_rays / process_camera_rays (vcm.cpp:193-258, 323-439) against the CUDA
+    stages on identical injected wavefronts.  Light pass: same survivors in the same order with identical RNG states and path
+    lengths, dVC/dVCM/dVM, throughputs and rays within 5e-4; the same camera-connection shadow rays (target pixel exact); the
+    same vertex-cache entries (LightVertices::add_vertex_to_cache).  Camera pass with the reference's cache installed on
+    both sides: same survivors / states, the same NEE + connection shadow rays (LightVertices::get_connect draws the same
+    vertices), and the same framebuffer contributions (emitter hits + HashGrid k-NN merging with the Epanechnikov kernel)."""
+    from tests import vcm_harness as vh
+    res = vh.run(scene, algo, w=64, h=64, waves=4)
+    assert (algo == "vcm_pt") == (len(res["light"]) == 0) and (algo == "lt") == (len(res["camera"]) == 0)
+    for r in res["light"]:
+        c = r["cont"]
+        assert c["ref"] == c["dev"] and c["only_one_side"] == 0, r
+        if c["ref"]:
+            assert c["same_order"] and c["rng_equal"] == 1.0 and c["len_equal"] == 1.0 and c["close"] >= 0.999, r
+        for part in ("connect", "cache"):
+            p = r[part]
+            assert p["ref"] == p["dev"] and p["only_one_side"] <= 0.002 * max(p["ref"], 1), r
+            if p["ref"]:
+                assert p["close"] >= 0.998, r
+        if algo == "ppm":
+            assert r["connect"]["ref"] == 0
+        if algo == "lt":
+            assert r["cache"]["ref"] == 0
+    for r in res["camera"]:
+        c = r["cont"]
+        assert c["ref"] == c["dev"] and c["only_one_side"] == 0, r
+        if c["ref"]:
+            assert c["same_order"] and c["rng_equal"] == 1.0 and c["len_equal"] == 1.0 and c["close"] >= 0.999, r
+        p = r["shadow"]
+        assert p["ref"] == p["dev"] and p["only_one_side"] <= 0.002 * max(p["ref"], 1), r
+        if p["ref"]:
+            assert p["close"] >= 0.998, r
+        assert r["fb_rel_err"] < 2e-3, r

@@ -16,6 +16,8 @@ def _rel(x, y):
 
 
 def _key(a):  # exact bit pattern of a float3 field, as a sortable key
+    if len(a) == 0:
+        return []
     return [bytes(x) for x in np.ascontiguousarray(a).view(np.uint8).reshape(len(a), -1)]
 
 
