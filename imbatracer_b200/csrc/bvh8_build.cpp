@@ -6,7 +6,9 @@
  *   1. parse the reference nodes into a generic tree (child boxes come from the parent's slots);
  *   2. split leaves holding more than 3 primitives (median split on the longest centroid axis) -- a Node8
  *      leaf child addresses at most 3 primitives;
- *   3. collapse to 8 children per node by repeatedly opening the inner child with the largest surface area;
+ *   3. collapse to 8-wide nodes with the SAH-optimal dynamic program of Ylitie, Karras, Laine 2017 (section 3): for every
+ *      node of the (binarised) tree the cheapest representation as a leaf of <= 3 primitives, as one 8-wide node, or as a
+ *      forest of i <= 7 roots handed to the parent; small sibling leaves are merged (node cost 1, primitive cost 0.5);
  *   4. assign children to slots so that `slot ^ ray octant` approximates front-to-back order (greedy
  *      assignment on centroid . octant-direction, Ylitie et al. 2017 section 4.2);
  *   5. quantise child boxes conservatively (always at least 1/64 cell of slack) to 8 bits on a power-of-two grid.
@@ -15,6 +17,7 @@
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 
@@ -195,10 +198,123 @@ void split_leaf(Tree& t, int tn) {
     split_leaf(t, l); split_leaf(t, r);
 }
 
+
+constexpr float COST_NODE = 1.0f;
+// cost of one primitive test relative to one node visit; tuning knob IMBA_COST_PRIM
+static const float COST_PRIM = getenv("IMBA_COST_PRIM") ? (float)atof(getenv("IMBA_COST_PRIM")) : 0.5f;
+
+/* SAH-optimal collapse.  Works on a binarised copy of the tree's topology: bin[n] = {left, right} for inner nodes. */
+struct Collapse {
+    Tree& t;
+    std::vector<int> left, right;          // binary children (-1 for leaves)
+    std::vector<int> prims_total;          // primitives in the subtree
+    std::vector<float> F, D;               // F[n*8 + i], i = 1..7; D[n*9 + j], j = 2..8
+    std::vector<unsigned char> Fkind, Dsplit; // Fkind: 0 leaf, 1 inner (i == 1) / 2 distribute, 3 fall back to i-1 (i >= 2)
+
+    explicit Collapse(Tree& tree) : t(tree) {}
+
+    int make_binary(int n) { // returns the id of a node with exactly two children (or a leaf), adding helper nodes for 3-4 children
+        TNode& nd = t.n[n];
+        if (nd.nkids <= 2) return n;
+        // fold: ((k0, k1), k2[, k3]) -- helper nodes get the union boxes
+        int a = nd.kids[0];
+        for (int k = 1; k + 1 < nd.nkids; ++k) {
+            const int h = (int)t.n.size(); t.n.emplace_back();
+            TNode& hn = t.n[h]; hn.nkids = 2; hn.kids[0] = a; hn.kids[1] = t.n[n].kids[k];
+            hn.b = t.n[a].b; hn.b.grow(t.n[t.n[n].kids[k]].b);
+            a = h;
+        }
+        TNode& nd2 = t.n[n];
+        const int last = nd2.kids[nd2.nkids - 1];
+        nd2.kids[0] = a; nd2.kids[1] = last; nd2.nkids = 2;
+        return n;
+    }
+
+    void run(int root) {
+        // binarise (iteratively; helper nodes are appended and already binary)
+        for (size_t i = 0; i < t.n.size(); ++i) if (t.n[i].nkids > 2) make_binary((int)i);
+        const size_t N = t.n.size();
+        left.assign(N, -1); right.assign(N, -1); prims_total.assign(N, 0);
+        F.assign(N * 8, 0.0f); D.assign(N * 9, 0.0f); Fkind.assign(N * 8, 0); Dsplit.assign(N * 9, 0);
+        // post-order over the tree rooted at `root`
+        std::vector<int> order, stack{ root };
+        while (!stack.empty()) { const int n = stack.back(); stack.pop_back(); order.push_back(n); for (int k = 0; k < t.n[n].nkids; ++k) stack.push_back(t.n[n].kids[k]); }
+        for (size_t oi = order.size(); oi-- > 0;) {
+            const int n = order[oi]; const TNode& nd = t.n[n];
+            const float A = nd.b.area();
+            if (nd.nkids == 0) {
+                prims_total[n] = nd.prim_count;
+                for (int i = 1; i <= 7; ++i) { F[n * 8 + i] = A * nd.prim_count * COST_PRIM; Fkind[n * 8 + i] = 0; }
+                continue;
+            }
+            if (nd.nkids == 1) { // dummy parent of a single leaf: behaves like its child
+                const int c = nd.kids[0]; left[n] = c; right[n] = -1; prims_total[n] = prims_total[c];
+                for (int i = 1; i <= 7; ++i) { F[n * 8 + i] = F[c * 8 + i]; Fkind[n * 8 + i] = 4; }
+                for (int j = 2; j <= 8; ++j) D[n * 9 + j] = F[c * 8 + std::min(j, 7)];
+                continue;
+            }
+            const int l = nd.kids[0], r = nd.kids[1];
+            left[n] = l; right[n] = r; prims_total[n] = prims_total[l] + prims_total[r];
+            for (int j = 2; j <= 8; ++j) {
+                float best = FLT_MAX; int bk = 1;
+                for (int k = 1; k < j; ++k) {
+                    if (k > 7 || j - k > 7) continue;
+                    const float c = F[l * 8 + k] + F[r * 8 + (j - k)];
+                    if (c < best) { best = c; bk = k; }
+                }
+                D[n * 9 + j] = best; Dsplit[n * 9 + j] = (unsigned char)bk;
+            }
+            const float inner = A * COST_NODE + D[n * 9 + 8];
+            const float leaf = prims_total[n] <= 3 ? A * prims_total[n] * COST_PRIM : FLT_MAX;
+            if (leaf <= inner) { F[n * 8 + 1] = leaf; Fkind[n * 8 + 1] = 0; } else { F[n * 8 + 1] = inner; Fkind[n * 8 + 1] = 1; }
+            for (int i = 2; i <= 7; ++i) {
+                if (D[n * 9 + i] < F[n * 8 + i - 1]) { F[n * 8 + i] = D[n * 9 + i]; Fkind[n * 8 + i] = 2; }
+                else { F[n * 8 + i] = F[n * 8 + i - 1]; Fkind[n * 8 + i] = 3; }
+            }
+        }
+    }
+
+    void gather_prims(int n, std::vector<int>& prims, std::vector<Box>& boxes) {
+        const TNode& nd = t.n[n];
+        if (nd.nkids == 0) { for (int i = 0; i < nd.prim_count; ++i) { prims.push_back(t.prims[nd.prim_first + i]); boxes.push_back(t.prim_box[nd.prim_first + i]); } return; }
+        for (int k = 0; k < nd.nkids; ++k) gather_prims(nd.kids[k], prims, boxes);
+    }
+
+    // Children (TNode ids: leaves or nodes that become 8-wide nodes) of the forest of <= i roots representing subtree n.
+    void collect(int n, int i, std::vector<int>& out) {
+        const TNode& nd = t.n[n];
+        if (nd.nkids == 0) { out.push_back(n); return; }
+        if (nd.nkids == 1) { collect(nd.kids[0], i, out); return; }
+        if (i > 7) i = 7;
+        const unsigned char kind = Fkind[n * 8 + i];
+        if (i == 1) {
+            if (kind == 1) { out.push_back(n); return; }
+            // merged leaf: a new leaf node holding all primitives of the subtree
+            std::vector<int> prims; std::vector<Box> boxes;
+            gather_prims(n, prims, boxes);
+            const int m = (int)t.n.size(); t.n.emplace_back();
+            TNode& leaf = t.n[m]; leaf.b = t.n[n].b; leaf.nkids = 0; leaf.prim_first = (int)t.prims.size(); leaf.prim_count = (int)prims.size();
+            t.prims.insert(t.prims.end(), prims.begin(), prims.end()); t.prim_box.insert(t.prim_box.end(), boxes.begin(), boxes.end());
+            out.push_back(m);
+            return;
+        }
+        if (kind == 3) { collect(n, i - 1, out); return; }
+        distribute(n, i, out);
+    }
+    // Children of subtree n when n itself is NOT a root: split the budget j between its two children.
+    void distribute(int n, int j, std::vector<int>& out) {
+        const TNode& nd = t.n[n];
+        if (nd.nkids == 1) { collect(nd.kids[0], std::min(j, 7), out); return; }
+        const int k = Dsplit[n * 9 + j];
+        const int l = nd.kids[0], r = nd.kids[1];
+        collect(l, k, out); collect(r, j - k, out);
+    }
+};
+
 inline int ilog2_floor(double v) { int e; frexp(v, &e); return e - 1; } // v in [2^(e-1), 2^e)
 
 struct Emitter {
-    Bvh8& out; const Tree& t; bool top_level;
+    Bvh8& out; Tree& t; Collapse* collapse; bool top_level;
     const std::vector<Tri48>* tri_store; const std::vector<const imba_instance_node*>* inst_store;
     const std::map<int, uint32_t>* mesh_roots; // reference root index -> Node8 index (top level only)
     int max_depth = 0;
@@ -221,21 +337,9 @@ struct Emitter {
         for (size_t qi = 0; qi < q.size(); ++qi) {
             const Work w = q[qi];
             max_depth = std::max(max_depth, w.depth);
-            // 3. collapse
-            std::vector<int> ch(t.n[w.tn].kids, t.n[w.tn].kids + t.n[w.tn].nkids);
-            for (;;) {
-                int best = -1; float ba = -1.0f;
-                for (size_t i = 0; i < ch.size(); ++i) {
-                    const TNode& c = t.n[ch[i]];
-                    if (c.nkids == 0 || ch.size() - 1 + c.nkids > 8) continue;
-                    const float a = c.b.area();
-                    if (a > ba) { ba = a; best = (int)i; }
-                }
-                if (best < 0) break;
-                const TNode c = t.n[ch[best]];
-                ch.erase(ch.begin() + best);
-                for (int k = 0; k < c.nkids; ++k) ch.push_back(c.kids[k]);
-            }
+            // 3. children of this 8-wide node from the collapse decisions
+            std::vector<int> ch;
+            collapse->distribute(w.tn, 8, ch);
             const int nc = (int)ch.size();
             Box nb; nb.reset();
             for (int c : ch) nb.grow(t.n[c].b);
@@ -357,11 +461,13 @@ bool imba_build_bvh8(int layout, int root, const void* nodes, const imba_vec4* t
         Tree mt;
         if (!build_tree(mp, in->next, mt)) return false;
         visited += mp.visited;
-        Emitter em{ out, mt, false, &tri_store, nullptr, nullptr };
+        Collapse mc(mt); mc.run(mt.root);
+        Emitter em{ out, mt, &mc, false, &tri_store, nullptr, nullptr };
         mesh_roots[in->next] = em.run();
         mesh_depth = std::max(mesh_depth, em.max_depth);
     }
-    Emitter em{ out, tt, true, nullptr, &inst_store, &mesh_roots };
+    Collapse tc(tt); tc.run(tt.root);
+    Emitter em{ out, tt, &tc, true, nullptr, &inst_store, &mesh_roots };
     out.top_root = em.run();
     out.max_depth = em.max_depth + mesh_depth;
     out.ref_node_count = visited;
