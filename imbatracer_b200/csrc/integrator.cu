@@ -120,6 +120,7 @@ static int pt_wavefront(imba_integrator* it, int cur, int capacity) {
     int rc = imba_scene_trace_ex(it->scene, rq, it->stream);
     if (rc != IMBA_OK) return rc;
     IMBA_CUDA(imba_sort_hits_by_material(it->part, it->hits, S.indices, S.material_count, (int*)it->shadow_states, 1, it->count[cur], 0, capacity, it->stream, false), IMBA_ERR_CUDA);
+    IMBA_CUDA(imba_pt_miss(S, it->rays[cur], (const PTState*)it->states[cur], it->part.indices, it->part.bin_start + S.material_count, it->count[cur], capacity, it->fb, it->stream), IMBA_ERR_CUDA);
     // survivors are pushed straight into the other queue by the shading kernel (fused compaction, replaces compact_rays)
     IMBA_CUDA(cudaMemsetAsync(it->count[cur ^ 1], 0, sizeof(int), it->stream), IMBA_ERR_CUDA);
     IMBA_CUDA(imba_pt_shade(S, it->rays[cur], it->hits, (PTState*)it->states[cur], it->part.indices, it->part.bin_start + S.material_count, it->count[cur], capacity,
@@ -217,6 +218,7 @@ extern "C" int imba_pt_shade_batch(imba_integrator* it, int count, const imba_ra
     IMBA_CUDA(cudaMemcpyAsync(it->states[0], h_states, (size_t)count * sizeof(PTState), cudaMemcpyHostToDevice, st), IMBA_ERR_CUDA);
     IMBA_CUDA(cudaMemcpyAsync(it->count[0], &count, 4, cudaMemcpyHostToDevice, st), IMBA_ERR_CUDA);
     IMBA_CUDA(imba_sort_hits_by_material(it->part, it->hits, S.indices, S.material_count, (int*)it->shadow_states, 1, it->count[0], 0, count, st), IMBA_ERR_CUDA);
+    IMBA_CUDA(imba_pt_miss(S, it->rays[0], (const PTState*)it->states[0], it->part.indices, it->part.bin_start + S.material_count, it->count[0], count, it->fb, st), IMBA_ERR_CUDA);
     IMBA_CUDA(imba_pt_shade(S, it->rays[0], it->hits, (PTState*)it->states[0], it->part.indices, it->part.bin_start + S.material_count, it->count[0], count,
                             it->shadow_rays, it->shadow_states, it->fb, it->cfg.max_path_len, it->d_stats, nullptr, nullptr, nullptr, st), IMBA_ERR_CUDA);
     // shadow queue: compact the valid slots (pixel_id >= 0) into rays[1] / states[1]

@@ -120,6 +120,24 @@ __global__ void __launch_bounds__(128) pt_shade_kernel(const DeviceShading S, fl
     if (!alive) states[idx].pixel_id = -1;
 }
 
+/* Rays that left the scene pick up the environment map (pt.cpp:95-116); misses are the last bin of the material sort. */
+__global__ void pt_miss_kernel(const DeviceShading S, const float4* rays, const PTState* states, const int* sorted, const int* hit_count_ptr,
+                               const int* queue_count_ptr, float* fb) {
+    const int i = *hit_count_ptr + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= *queue_count_ptr) return;
+    const int idx = sorted[i];
+    const PTState st = states[idx];
+    const V3 out_dir = normalize(v3(rays[2 * idx + 1]));
+    float pdf_direct_w, pdf_emit_w;
+    const V3 li = env_radiance(S, out_dir, pdf_direct_w, pdf_emit_w);
+    const float pdf_lightpick = 1.0f / S.light_count;
+    const float pdf_di = pdf_direct_w * pdf_lightpick;
+    const float pdf_hit = st.last_pdf;
+    const bool first_or_specular = (st.bounces_spec & 0x7fffffffu) == 0 || (st.bounces_spec >> 31) != 0;
+    const float mis = first_or_specular ? 1.0f : (pdf_hit / (pdf_hit + pdf_di));
+    add_contribution(fb, st.pixel_id, v3(st.tr, st.tg, st.tb) * li * mis);
+}
+
 /* Integrator::estimate_pixel_size (integrator.cpp:14-71): corner rays of every 8th pixel */
 __global__ void probe_raygen_kernel(DevCamera cam, float4* rays, int count) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -162,6 +180,13 @@ cudaError_t imba_pt_shade(const DeviceShading& S, float4* rays, const int4* hits
                           int* out_count, cudaStream_t st) {
     if (capacity <= 0) return cudaSuccess;
     pt_shade_kernel<<<(capacity + 127) / 128, 128, 0, st>>>(S, rays, hits, states, sorted, hit_count_ptr, queue_count_ptr, shadow_rays, shadow_states, fb, max_path_len, ray_stats, out_rays, out_states, out_count);
+    return cudaGetLastError();
+}
+
+cudaError_t imba_pt_miss(const DeviceShading& S, const float4* rays, const PTState* states, const int* sorted, const int* hit_count_ptr, const int* queue_count_ptr,
+                         int capacity, float* fb, cudaStream_t st) {
+    if (capacity <= 0 || S.env_tex < 0) return cudaSuccess;
+    pt_miss_kernel<<<(capacity + 255) / 256, 256, 0, st>>>(S, rays, states, sorted, hit_count_ptr, queue_count_ptr, fb);
     return cudaGetLastError();
 }
 

@@ -42,6 +42,7 @@ struct DeviceShading {
     const float4* texels;
     int material_count, light_count, instance_count, texture_count;
     float bs_cx, bs_cy, bs_cz, bs_radius, bs_inv_radius_sqr;
+    int   env_tex; float env_intensity;   // environment map (light.h:361-485): texture index or -1
 };
 
 /* ---- RNG ------------------------------------------------------------------------------------------------- */
@@ -302,6 +303,37 @@ __device__ __forceinline__ V3 emitter_radiance(V3 intensity, float area, V3 out_
     return intensity;
 }
 
+/* ---- environment map (EnvMap, light.h:361-485; lat-long image, uniform sampling: the importance tables built by the
+ * reference's constructor are never used, light.h:433-435,466) ----------------------------------------------------------- */
+__device__ __forceinline__ V3 env_lookup(const DeviceShading& S, float s, float t) {
+    const int4 d = __ldg(S.textures + S.env_tex);
+    const int x = (int)(s * (d.x - 1)), y = (int)(t * (d.y - 1));
+    return S.env_intensity * v3(__ldg(S.texels + d.z + y * d.x + x));
+}
+/* EnvMap::radiance (light.h:443-453); note the reference divides by sinf(t) with t in [0, 1], not by sin(theta) */
+__device__ __forceinline__ V3 env_radiance(const DeviceShading& S, V3 out_dir, float& pdf_direct_w, float& pdf_emit_w) {
+    float phi = atan2f(out_dir.x, out_dir.z);
+    phi = (phi < 0.0f) ? (phi + 2.0f * IMBA_PI) : phi;
+    const float s = phi / (2.0f * IMBA_PI);
+    const float t = acosf(out_dir.y) / IMBA_PI;
+    pdf_direct_w = 1.0f / (2.0f * IMBA_PI * IMBA_PI * sinf(t));
+    pdf_emit_w = (1.0f / IMBA_PI) * S.bs_inv_radius_sqr * pdf_direct_w;
+    return env_lookup(S, s, t);
+}
+/* EnvMap::sample_dir / sample_uv (light.h:458-485) */
+__device__ __forceinline__ V3 env_sample_dir(const DeviceShading& S, Rng& rng, V3& dir, float& pdf) {
+    const int4 d = __ldg(S.textures + S.env_tex);
+    pdf = 1.0f / float(d.x * d.y);
+    const float ux = rng.uniform();
+    const float uy = rng.uniform();
+    pdf *= float(d.x * d.y);
+    const V3 color = env_lookup(S, ux, uy);
+    const float theta = IMBA_PI * uy, sin_theta = sinf(theta), phi = 2.0f * IMBA_PI * ux;
+    dir = v3(sin_theta * sinf(phi), cosf(theta), sin_theta * cosf(phi));
+    if (sin_theta != 0.0f) pdf /= 2.0f * IMBA_PI * IMBA_PI * sin_theta; else pdf = 0.0f;
+    return color;
+}
+
 /* ---- lights (light.h) --------------------------------------------------------------------------------- */
 struct DirectSample { V3 dir; float distance; V3 radiance; float cos_out, pdf_emit_w, pdf_direct_w; bool delta; };
 struct EmitSample { V3 pos, dir, radiance; float cos_out, pdf_emit_w, pdf_direct_a; bool delta, finite; };
@@ -312,8 +344,13 @@ __device__ __forceinline__ DirectSample light_sample_direct(const DeviceShading&
     const int kind = __float_as_int(i4.w);
     const V3 intensity = v3(i4);
     DirectSample s;
-    s.delta = kind != LIGHT_TRIANGLE;
-    if (kind == LIGHT_TRIANGLE) {
+    s.delta = kind != LIGHT_TRIANGLE && kind != LIGHT_ENV;
+    if (kind == LIGHT_ENV) { // EnvLight::sample_direct (light.h:516-530)
+        float pdf; V3 dir;
+        const V3 radiance = env_sample_dir(S, rng, dir, pdf);
+        s.dir = dir; s.distance = FLT_MAX; s.radiance = radiance / pdf; s.pdf_direct_w = pdf;
+        s.pdf_emit_w = (1.0f / IMBA_PI) * S.bs_inv_radius_sqr * pdf; s.cos_out = 1.0f;
+    } else if (kind == LIGHT_TRIANGLE) {
         const float area = p0.w;
         const float r2 = rng.uniform(), r1 = rng.uniform();
         const float sq = sqrtf(r1), u = 1.0f - sq, v = r2 * sq;
@@ -369,8 +406,18 @@ __device__ __forceinline__ EmitSample light_sample_emit(const DeviceShading& S, 
     const int kind = __float_as_int(i4.w);
     const V3 intensity = v3(i4);
     EmitSample s;
-    s.delta = kind != LIGHT_TRIANGLE; s.finite = kind != LIGHT_DIRECTIONAL;
-    if (kind == LIGHT_TRIANGLE) {
+    s.delta = kind != LIGHT_TRIANGLE && kind != LIGHT_ENV; s.finite = kind != LIGHT_DIRECTIONAL && kind != LIGHT_ENV;
+    if (kind == LIGHT_ENV) { // EnvLight::sample_emit (light.h:494-513)
+        float pdf; V3 dir;
+        const V3 radiance = env_sample_dir(S, rng, dir, pdf);
+        dir *= -1.0f;
+        const float d2 = rng.uniform(), d1 = rng.uniform();
+        const float2 disc = concentric_disc(d1, d2);
+        V3 tangent, binormal; local_coordinates(dir, tangent, binormal);
+        s.pos = v3(S.bs_cx, S.bs_cy, S.bs_cz) + S.bs_radius * (-dir + binormal * disc.x + tangent * disc.y);
+        s.dir = dir; s.pdf_direct_a = pdf; s.pdf_emit_w = (1.0f / IMBA_PI) * S.bs_inv_radius_sqr * pdf; s.cos_out = 1.0f;
+        s.radiance = radiance / s.pdf_emit_w;
+    } else if (kind == LIGHT_TRIANGLE) {
         const float area = p0.w;
         const float r2 = rng.uniform(), r1 = rng.uniform();
         const float sq = sqrtf(r1), u = 1.0f - sq, v = r2 * sq;

@@ -69,6 +69,8 @@ int imba_shading_upload(imba_scene* s, const imba_scene_desc* d) {
     v.textures = up<int4>(st, tex.data(), tex.size(), ok);
     v.texels = up<float4>(st, d->texels, (size_t)d->texel_count, ok);
     v.material_count = d->material_count; v.light_count = d->light_count; v.instance_count = d->instance_count; v.texture_count = d->texture_count;
+    v.env_tex = d->env_tex; v.env_intensity = d->env_intensity;
+    if (v.env_tex >= d->texture_count) { imba_set_error("env_tex out of range"); return IMBA_ERR_INVALID; }
     v.bs_cx = d->bsphere_center[0]; v.bs_cy = d->bsphere_center[1]; v.bs_cz = d->bsphere_center[2];
     v.bs_radius = d->bsphere_radius; v.bs_inv_radius_sqr = 1.0f / (d->bsphere_radius * d->bsphere_radius);
     if (!ok) { imba_set_error("shading data upload failed: %s", cudaGetErrorString(cudaGetLastError())); return IMBA_ERR_CUDA; }

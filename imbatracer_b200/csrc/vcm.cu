@@ -505,6 +505,24 @@ __global__ void __launch_bounds__(128) vcm_camera_shade_kernel(const DeviceShadi
     } else states[idx].pixel_id = -1;
 }
 
+/* Camera paths that leave the scene pick up the environment map (vcm.cpp:345-366); not for the VCM-style PT. */
+template <int ALGO>
+__global__ void vcm_camera_miss_kernel(const DeviceShading S, const float4* rays, const VCMState* states, const int* sorted, const int* hit_count_ptr,
+                                       const int* queue_count_ptr, float* fb) {
+    const int i = *hit_count_ptr + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= *queue_count_ptr) return;
+    const int idx = sorted[i];
+    const VCMState st = states[idx];
+    const V3 out_dir = normalize(v3(rays[2 * idx + 1]));
+    float pdf_direct_w, pdf_emit_w;
+    const V3 li = env_radiance(S, out_dir, pdf_direct_w, pdf_emit_w);
+    const float pdf_lightpick = 1.0f / S.light_count;
+    const float pdf_di = pdf_direct_w * pdf_lightpick, pdf_e = pdf_emit_w * pdf_lightpick;
+    const float mis_weight_camera = pdf_di * st.dVCM + pdf_e * st.dVC;
+    const float mis_weight = ALGO == IMBA_ALGO_PPM ? 1.0f : (1.0f / (mis_weight_camera + 1.0f));
+    add_contribution(fb, st.pixel_id, v3(st.tr, st.tg, st.tb) * li * mis_weight);
+}
+
 template <int ALGO>
 cudaError_t light_shade(const VcmLaunch& a, cudaStream_t st) {
     vcm_light_shade_kernel<ALGO><<<(a.capacity + 127) / 128, 128, 0, st>>>(*a.S, a.P, a.cam, a.rays, a.hits, a.states, a.sorted, a.hit_count_ptr, a.queue_count_ptr,
@@ -513,6 +531,8 @@ cudaError_t light_shade(const VcmLaunch& a, cudaStream_t st) {
 }
 template <int ALGO>
 cudaError_t camera_shade(const VcmLaunch& a, cudaStream_t st) {
+    if (a.S->env_tex >= 0 && ALGO != IMBA_ALGO_VCM_PT)
+        vcm_camera_miss_kernel<ALGO><<<(a.capacity + 255) / 256, 256, 0, st>>>(*a.S, a.rays, a.states, a.sorted, a.hit_count_ptr, a.queue_count_ptr, a.fb);
     vcm_camera_shade_kernel<ALGO><<<(a.capacity + 127) / 128, 128, 0, st>>>(*a.S, a.P, a.rays, a.hits, a.states, a.sorted, a.hit_count_ptr, a.queue_count_ptr, a.shadow_rays,
                                                                            a.shadow_states, a.cache, a.grid, a.cells, a.table, a.photons, a.fb, a.ray_stats, a.out_rays, a.out_states, a.out_count);
     return cudaGetLastError();

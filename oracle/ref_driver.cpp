@@ -296,7 +296,16 @@ int ref_scene_export(void* h, imba_scene_desc* d) {
     d->light_count = (int)rs->lights.size(); d->lights = rs->lights.data();
     d->texture_count = (int)rs->textures.size(); d->textures = rs->textures.data();
     d->texels = rs->texels.data(); d->texel_count = (int64_t)rs->texels.size() / 4;
-    d->env_tex = -1; d->env_intensity = 0.0f; // TODO env maps (Car scene only; HDR missing)
+    d->env_tex = -1; d->env_intensity = 0.0f;
+    if (sc.env_map()) { // EnvMap keeps its own image (light.h:476): exported as one more texture
+        const Image& img = sc.env_map()->img_;
+        imba_texture o; o.width = img.width(); o.height = img.height(); o.offset = (int64_t)rs->texels.size() / 4;
+        for (int i = 0; i < img.width() * img.height(); ++i) { const rgba& p = img.pixels()[i]; rs->texels.insert(rs->texels.end(), { p.x, p.y, p.z, p.w }); }
+        rs->textures.push_back(o);
+        d->env_tex = (int)rs->textures.size() - 1; d->env_intensity = sc.env_map()->intensity_;
+        d->texture_count = (int)rs->textures.size(); d->textures = rs->textures.data();
+        d->texels = rs->texels.data(); d->texel_count = (int64_t)rs->texels.size() / 4;
+    }
     d->bsphere_center[0] = sc.bounding_sphere().center.x; d->bsphere_center[1] = sc.bounding_sphere().center.y;
     d->bsphere_center[2] = sc.bounding_sphere().center.z; d->bsphere_radius = sc.bounding_sphere().radius;
     if (rs->gpu_layout) {
@@ -503,6 +512,21 @@ int ref_scene_add_test_textures(void* h, uint64_t seed) {
         for (size_t v = 0; v < mesh.vertex_count(); ++v) { tc[v].x = 4.0f * rng.random_float() - 1.5f; tc[v].y = 4.0f * rng.random_float() - 1.5f; }
     }
     return changed;
+}
+
+/// TEST HOOK: adds a procedural environment map + EnvLight (what build_scene.cpp:505-527 does for an `env` line; the only
+/// scene of the reference that has one, Car, lacks its HDR file here).
+int ref_scene_add_test_envmap(void* h, uint64_t seed, float intensity) {
+    auto rs = (RefScene*)h; Scene& sc = *rs->scene;
+    if (sc.env_map()) return 0;
+    RNG rng(seed);
+    const int w = 24, hgt = 12;
+    Image img(w, hgt);
+    for (int y = 0; y < hgt; ++y) for (int x = 0; x < w; ++x)
+        img(x, y) = rgba(0.3f + 0.7f * rng.random_float(), 0.4f + 0.5f * (float)y / hgt, 0.2f + 0.8f * (float)x / w, 1.0f);
+    sc.set_env_map(new EnvMap(img, intensity, sc.bounding_sphere()));
+    sc.lights().emplace_back(new EnvLight(sc.env_map(), sc.bounding_sphere()));
+    return 1;
 }
 
 /// RNG known-answer helper (render/random.h:15-47).

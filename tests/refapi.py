@@ -62,6 +62,7 @@ def ref():
         L.ref_seed_states.restype = None; L.ref_seed_states.argtypes = [C.c_uint64, i32, i32, i32, vp]
         L.ref_struct_sizes.argtypes = [vp]
         L.ref_scene_add_test_textures.argtypes = [vp, C.c_uint64]
+        L.ref_scene_add_test_envmap.argtypes = [vp, C.c_uint64, f32]
         L.ref_vcm_stage.argtypes = [vp, i32, i32, i32, f32, i32, i32, i32, i32, f32, i32, i32, i32, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp]
         _ref = L
     return _ref
@@ -143,6 +144,10 @@ class RefScene:
     def add_test_textures(self, seed=99):
         """Procedural colour / bump textures + texcoords on the reference side (oracle/ref_driver.cpp); export with flat() afterwards."""
         return self.L.ref_scene_add_test_textures(self.h, seed)
+
+    def add_test_envmap(self, seed=5, intensity=0.8):
+        """Procedural lat-long environment map + EnvLight on the reference side; export with flat() afterwards."""
+        return self.L.ref_scene_add_test_envmap(self.h, seed, intensity)
 
     def flat(self, name="") -> FlatScene:
         d = abi.SceneDesc()

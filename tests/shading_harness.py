@@ -57,11 +57,14 @@ def compare_wave(ref_out, dev_out, tol=2e-4):
     return out
 
 
-def run_waves(scene_name, w=96, h=96, waves=4, max_path_len=10, layout="gpu", verbose=False, textured=False):
+def run_waves(scene_name, w=96, h=96, waves=4, max_path_len=10, layout="gpu", verbose=False, textured=False, envmap=False):
     """Wave k feeds the REFERENCE's continuation queue of wave k-1 (traced by the oracle) to both implementations."""
     from tests.conftest import load_scene
     flat = load_scene(scene_name, layout)
     rs = refapi.RefScene(os.path.join(refapi.REF_SCENES, "cornell", scene_name + ".scene"), layout == "gpu")
+    if envmap:    # environment map + EnvLight injected on the reference side
+        assert rs.add_test_envmap() == 1
+        flat = rs.flat(scene_name)
     if textured:  # textures, bump maps and texcoords injected on the reference side, exported to the device scene
         assert rs.add_test_textures() > 0
         flat = rs.flat(scene_name)

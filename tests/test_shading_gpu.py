@@ -53,6 +53,22 @@ def test_textured_and_bump_mapped_shading_matches_reference(scene):
             assert r["shadow_close"] >= 0.995, r
 
 
+@needs_ref
+def test_environment_map_shading_matches_reference():
+    """EnvMap::radiance on escaped rays (pt.cpp:95-116) and EnvLight::sample_direct as one of the NEE lights
+    (light.h:443-453, 516-530): a procedural environment map is added to the reference's scene and exported."""
+    from tests import shading_harness as sh
+    res = sh.run_waves("cornell_org", w=96, h=96, waves=4, envmap=True)
+    for r in res[1:]:
+        assert r["ref_cont"] == r["dev_cont"] and r["ref_shadow"] == r["dev_shadow"], r
+        if r["ref_cont"]:
+            assert r["cont_same_order"] and r["cont_rng_equal"] == 1.0 and r["cont_flags_equal"] == 1.0 and r["cont_close"] >= 0.995, r
+        if r["ref_shadow"]:
+            assert r["shadow_close"] >= 0.995, r
+        assert r["fb_ref_sum"] > 0 and r["fb_max_abs_err"] <= 2e-4 * max(1.0, r["fb_ref_sum"]), r
+    assert res[1]["fb_ref_sum"] > 3000  # wave 0: emitter hits (2541) plus environment light through the open front
+
+
 def gamma_rmse(a, b):
     return float(np.sqrt(np.mean((np.clip(a, 0, 1) ** 0.5 - np.clip(b, 0, 1) ** 0.5) ** 2)))
 

@@ -115,3 +115,19 @@ def test_vcm_stages_match_reference_wavefronts(scene, algo):
         if p["ref"]:
             assert p["close"] >= 0.998, r
         assert r["fb_rel_err"] < 2e-3, r
+
+
+@needs_ref
+@pytest.mark.parametrize("algo", ["vcm", "lt", "ppm"])
+def test_vcm_stages_with_environment_light(algo):
+    """EnvLight::sample_emit for light paths (light.h:494-513, infinite light: finite_light = 0) and the environment term of
+    escaped camera paths (vcm.cpp:345-366), through the same stage harness."""
+    from tests import vcm_harness as vh
+    res = vh.run("cornell_org", algo, w=64, h=64, waves=3, envmap=True)
+    for r in res["light"] + res["camera"]:
+        c = r["cont"]
+        assert c["ref"] == c["dev"] and c["only_one_side"] == 0, r
+        if c["ref"]:
+            assert c["same_order"] and c["rng_equal"] == 1.0 and c["len_equal"] == 1.0 and c["close"] >= 0.998, r
+    for r in res["camera"]:
+        assert r["fb_rel_err"] < 2e-3 and r["fb_ref_sum"] > 0, r

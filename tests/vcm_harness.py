@@ -54,10 +54,13 @@ def compare_keyed(ra, da, key_field, fields, tol):
     return out
 
 
-def run(scene_name, algo, w=64, h=64, waves=4, iteration=3, layout="gpu", tol=5e-4, verbose=False):
+def run(scene_name, algo, w=64, h=64, waves=4, iteration=3, layout="gpu", tol=5e-4, verbose=False, envmap=False):
     from tests.conftest import load_scene
     flat = load_scene(scene_name, layout)
     rs = refapi.RefScene(os.path.join(refapi.REF_SCENES, "cornell", scene_name + ".scene"), layout == "gpu")
+    if envmap:
+        assert rs.add_test_envmap() == 1
+        flat = rs.flat(scene_name)
     scene = api.Scene(flat)
     n_light = w * h // 2
     integ = api.Integrator(scene, api.render_settings(flat, algo, w, h, light_path_count=n_light))
