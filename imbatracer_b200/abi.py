@@ -129,6 +129,10 @@ def lib():
     L.imba_bvh8_arrays.argtypes = [vp, C.POINTER(vp), C.POINTER(i64), C.POINTER(vp), C.POINTER(i64), C.POINTER(vp),
                                    C.POINTER(i64), C.POINTER(C.c_uint32), C.POINTER(i32)]
     f32, u32 = C.c_float, C.c_uint32
+    L.imba_bvh_cache_open.restype = vp; L.imba_bvh_cache_open.argtypes = [C.c_char_p]
+    L.imba_bvh_cache_close.restype = None; L.imba_bvh_cache_close.argtypes = [vp]
+    L.imba_bvh_cache_block.argtypes = [vp, i32, C.POINTER(vp), C.POINTER(u32), C.POINTER(vp), C.POINTER(u32)]
+    L.imba_bvh_cache_append.argtypes = [C.c_char_p, i32, vp, u32, vp, u32]
     L.imba_accel_build.restype = vp; L.imba_accel_build.argtypes = [C.POINTER(SceneDesc)]
     L.imba_accel_free.restype = None; L.imba_accel_free.argtypes = [vp]
     L.imba_accel_arrays.argtypes = [vp, C.POINTER(vp), C.POINTER(i64), C.POINTER(vp), C.POINTER(i64), C.POINTER(vp), C.POINTER(i64), C.POINTER(i32)]

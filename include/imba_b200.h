@@ -223,6 +223,16 @@ int  imba_accel_arrays(const imba_accel* a, const void** nodes, int64_t* node_co
                        const void** inst_nodes, int64_t* inst_node_count, int32_t* root);
 void imba_accel_free(imba_accel* a);
 
+/* The reference's per-mesh `.bvh` cache files (loaders/load_bvh.cpp:12-43, 144-302): magic 0x313F1A57, blocks of
+ * {u64 size, u32 type, u32 node_count, u32 prim_count, nodes, prims}; type 1 = BVH2 (imba_node2 + Vec4 triples), type 2 =
+ * MBVH4 (imba_node4 + Vec4 packets), indices file-local; type 3 (new) = this library's Node8 (80 B) + Tri48 (48 B).
+ * prim_count counts Vec4 for types 1/2 and triangles for type 3.  Unknown block types are skipped on read. */
+typedef struct imba_bvh_file imba_bvh_file;
+imba_bvh_file* imba_bvh_cache_open(const char* path);
+int  imba_bvh_cache_block(const imba_bvh_file* f, int type, const void** nodes, uint32_t* node_count, const void** prims, uint32_t* prim_count);
+int  imba_bvh_cache_append(const char* path, int type, const void* nodes, uint32_t node_count, const void* prims, uint32_t prim_count);
+void imba_bvh_cache_close(imba_bvh_file* f);
+
 /* ------------------------------------------------------------------------------------------
  * L2: ray-queue primitives on device arrays (render/scheduling/ray_queue.h:161-244)
  * ---------------------------------------------------------------------------------------- */

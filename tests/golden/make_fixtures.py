@@ -8,6 +8,7 @@
   hits_<name>.npz             oracle closest-hit / occlusion results for the seeded ray batch of tests/raygen.py
   ref_<image>_128.npy         the reference's converged golden PNGs (test/references/*.png), box-filtered to 128x128 in
                               linear radiance (PNG = 8 bit, gamma 0.5, store_png.h:59-62)
+  CornellBox-*.bvh            acceleration-structure caches written by the reference's own loader (load_bvh.cpp)
   rng_kat.npz                 known-answer values of the reference's RNG (render/random.h:15-47) and of the primary-ray
                               seeding (ray_gen.h:57-72), produced by the unmodified reference headers
 Also copies the reference's Cornell scenes to oracle/_ref/scenes (git-ignored scratch; the reference loader writes .bvh
@@ -52,6 +53,11 @@ def main():
             out[f"occluded_{tag}"] = np.packbits(occl["tri_id"] >= 0)
         np.savez_compressed(os.path.join(HERE, f"hits_{name}.npz"), **out)
         print(name, "tris", flat[False].tri_count, "rays", len(rays))
+
+    # .bvh caches the reference's loader wrote next to the meshes while loading (render/scene.cpp:67, loaders/load_bvh.cpp)
+    import shutil
+    for f in ("CornellBox-Original.bvh", "CornellBox-Specular.bvh"):
+        shutil.copy(os.path.join(scenes, "cornell", f), os.path.join(HERE, f))
 
     from PIL import Image
     for img in IMAGES:
