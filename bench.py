@@ -256,6 +256,19 @@ def run_extra_scenes(rank):
             t0 = time.perf_counter(); integ.render(4); integ.sync(); dt = time.perf_counter() - t0
             r["vcm_1280x720"] = {"ms_per_iteration": dt / 4 * 1e3, "samples_per_s": 1280 * 720 * 4 / dt, "light_paths": 1280 * 720 // 2, "connections": 1, "knn": 10}
             integ.close()
+        if label.startswith("terrain"):  # row f1: the same mesh through the GPU builder (csrc/lbvh.cu)
+            t0 = time.perf_counter(); procedural.build_accel(flat, gpu=True); wall = time.perf_counter() - t0
+            scene2 = api.Scene(flat)
+            for _ in range(3):
+                scene2.trace(d, hits)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(5):
+                scene2.trace(d, hits)
+            e1.record(); torch.cuda.synchronize()
+            r["gpu_lbvh"] = {"build_device_ms": flat.build_seconds * 1e3, "build_call_s": wall, "closest_mrays_s": n * 5 / e0.elapsed_time(e1) / 1e3}
+            scene2.close()
         out[label] = r
         scene.close()
     return out

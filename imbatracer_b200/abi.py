@@ -134,6 +134,7 @@ def lib():
     L.imba_bvh_cache_block.argtypes = [vp, i32, C.POINTER(vp), C.POINTER(u32), C.POINTER(vp), C.POINTER(u32)]
     L.imba_bvh_cache_append.argtypes = [C.c_char_p, i32, vp, u32, vp, u32]
     L.imba_accel_build.restype = vp; L.imba_accel_build.argtypes = [C.POINTER(SceneDesc)]
+    L.imba_accel_build_gpu.restype = vp; L.imba_accel_build_gpu.argtypes = [C.POINTER(SceneDesc), C.POINTER(C.c_float)]
     L.imba_accel_free.restype = None; L.imba_accel_free.argtypes = [vp]
     L.imba_accel_arrays.argtypes = [vp, C.POINTER(vp), C.POINTER(i64), C.POINTER(vp), C.POINTER(i64), C.POINTER(vp), C.POINTER(i64), C.POINTER(i32)]
     L.imba_integrator_create.restype = vp; L.imba_integrator_create.argtypes = [vp, C.POINTER(RenderSettings)]

@@ -129,11 +129,6 @@ struct Builder {
 
 } // namespace
 
-struct imba_accel {
-    std::vector<imba_node2> nodes; std::vector<imba_vec4> tris; std::vector<imba_instance_node> inst_nodes;
-    int root = 0;
-};
-
 extern "C" void imba_accel_free(imba_accel* a) { delete a; }
 
 extern "C" imba_accel* imba_accel_build(const imba_scene_desc* d) {
@@ -171,11 +166,22 @@ extern "C" imba_accel* imba_accel_build(const imba_scene_desc* d) {
         mesh_root[m] = b.run();
         mesh_box[m].reset(); for (int t = 0; t < nt; ++t) mesh_box[m].grow(boxes[t]);
     }
+    std::vector<float> boxes6(6 * (size_t)d->mesh_count);
+    for (int m = 0; m < d->mesh_count; ++m) for (int a = 0; a < 3; ++a) { boxes6[6 * m + a] = mesh_box[m].lo[a]; boxes6[6 * m + 3 + a] = mesh_box[m].hi[a]; }
+    if (imba_accel_finish_top(out, d, mesh_root.data(), boxes6.data()) != IMBA_OK) { delete out; return nullptr; }
+    return out;
+}
+
+/* Top level over the instance boxes, appended after the mesh nodes (shared by the host and the GPU mesh builders). */
+int imba_accel_finish_top(imba_accel* out, const imba_scene_desc* d, const int* mesh_root_in, const float* mesh_box6) {
+    std::vector<int> mesh_root(mesh_root_in, mesh_root_in + d->mesh_count);
+    std::vector<Box3> mesh_box(d->mesh_count);
+    for (int m = 0; m < d->mesh_count; ++m) for (int a = 0; a < 3; ++a) { mesh_box[m].lo[a] = mesh_box6[6 * m + a]; mesh_box[m].hi[a] = mesh_box6[6 * m + 3 + a]; }
     // ---- top level over instance boxes (cpu_adapter.cpp:233-249: centre +- |M| * half extent) ---------------------------
     std::vector<Box3> ibox(d->instance_count);
     for (int i = 0; i < d->instance_count; ++i) {
         const imba_instance& in = d->instances[i];
-        if (in.mesh_id < 0 || in.mesh_id >= d->mesh_count) { imba_set_error("instance %d refers to mesh %d", i, in.mesh_id); delete out; return nullptr; }
+        if (in.mesh_id < 0 || in.mesh_id >= d->mesh_count) { imba_set_error("instance %d refers to mesh %d", i, in.mesh_id); return IMBA_ERR_INVALID; }
         const Box3& mb = mesh_box[in.mesh_id];
         for (int r = 0; r < 3; ++r) {
             float c = in.mat[4 * r + 3], e = 0.0f;
@@ -199,7 +205,7 @@ extern "C" imba_accel* imba_accel_build(const imba_scene_desc* d) {
     // top-level nodes live in the same array, after the mesh nodes (scene.cpp:168-176); indices are absolute already
     Builder top(ibox.data(), d->instance_count, 1, out->nodes, 0, &ileaf);
     out->root = top.run();
-    return out;
+    return IMBA_OK;
 }
 
 /* Points the acceleration-structure fields of `d` at the arrays owned by `a` (valid until imba_accel_free). */

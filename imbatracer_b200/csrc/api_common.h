@@ -62,4 +62,11 @@ void imba_scene_trace_args(const imba_scene* s, TraceArgs* a);
 int imba_scene_trace(imba_scene* s, const imba_ray* d_rays, imba_hit* d_hits, int count, int any_hit, uint32_t* d_counters,
                      cudaStream_t stream);
 
+/* Two-level structure in the reference's BVH2 layout (accel_build.cpp, lbvh.cu). */
+struct imba_accel {
+    std::vector<imba_node2> nodes; std::vector<imba_vec4> tris; std::vector<imba_instance_node> inst_nodes;
+    int root = 0;
+};
+int imba_accel_finish_top(imba_accel* out, const imba_scene_desc* d, const int* mesh_root, const float* mesh_box6);
+
 #endif

@@ -9,17 +9,20 @@ from . import abi
 from .scene import FlatScene
 
 
-def build_accel(flat: FlatScene):
-    """Runs imba_accel_build on `flat` (meshes + instances) and stores the BVH2-layout arrays in it."""
+def build_accel(flat: FlatScene, gpu=False):
+    """Runs imba_accel_build (host, binned SAH) or imba_accel_build_gpu (device, linear BVH) on `flat` (meshes + instances) and
+    stores the BVH2-layout arrays in it; flat.build_seconds = device time of the GPU mesh builds."""
     L = abi.lib()
     a = flat.arrays
     for k, dt in (("nodes", abi.NODE2), ("tris", np.float32), ("inst_nodes", abi.INSTANCE_NODE)):
         a.setdefault(k, np.zeros(0, dt))
     flat.accel_layout = 1
     d = flat.desc()
-    h = L.imba_accel_build(C.byref(d))
+    secs = (C.c_float * 2)()
+    h = L.imba_accel_build_gpu(C.byref(d), secs) if gpu else L.imba_accel_build(C.byref(d))
     if not h:
         raise RuntimeError("imba_accel_build failed: " + abi.last_error())
+    flat.build_seconds = float(secs[0])
     p = [C.c_void_p() for _ in range(3)]; n = [C.c_int64() for _ in range(3)]; root = C.c_int32()
     abi.check(L.imba_accel_arrays(h, p[0], n[0], p[1], n[1], p[2], n[2], root))
 

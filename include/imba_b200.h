@@ -218,6 +218,9 @@ int  imba_bvh8_arrays(const imba_bvh8* h, const void** nodes, int64_t* node_coun
  * mesh_*, vertices, indices, instances of `desc`; imba_accel_fill points desc's accel fields at the result. */
 typedef struct imba_accel imba_accel;
 imba_accel* imba_accel_build(const imba_scene_desc* desc);
+/* Same result type with the per-mesh trees built on the current CUDA device (linear BVH: Morton codes, radix sort, parallel
+ * hierarchy, bottom-up refit; csrc/lbvh.cu); out_seconds[0] (optional) receives the device time of the mesh builds. */
+imba_accel* imba_accel_build_gpu(const imba_scene_desc* desc, float* out_seconds);
 int  imba_accel_fill(const imba_accel* a, imba_scene_desc* desc);
 int  imba_accel_arrays(const imba_accel* a, const void** nodes, int64_t* node_count, const void** tris, int64_t* tri_vec4_count,
                        const void** inst_nodes, int64_t* inst_node_count, int32_t* root);

@@ -42,4 +42,6 @@ if "instanced" in which:
     run(s, label="cornell_water x 2744 instances")
 if "terrain" in which:
     t0 = time.time(); s = procedural.terrain(int(os.environ.get("TERRAIN_N", "1536"))); print("build terrain", round(time.time() - t0, 1), "s", flush=True)
-    run(s, label="terrain")
+    run(s, label="terrain (host binned SAH)")
+    t0 = time.time(); procedural.build_accel(s, gpu=True); print("gpu lbvh: device", round(s.build_seconds * 1e3, 2), "ms, whole call", round(time.time() - t0, 2), "s", flush=True)
+    run(s, label="terrain (GPU LBVH)")
