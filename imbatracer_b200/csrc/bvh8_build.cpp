@@ -17,6 +17,8 @@
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
+#include <chrono>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <map>
@@ -455,16 +457,24 @@ bool imba_build_bvh8(int layout, int root, const void* nodes, const imba_vec4* t
     std::map<int, uint32_t> mesh_roots; int mesh_depth = 0;
     for (const imba_instance_node* in : inst_store) {
         if (mesh_roots.count(in->next)) continue;
+        const auto t0 = std::chrono::steady_clock::now();
         std::vector<Tri48> tri_store;
         Parser mp{ layout, nodes, tris, inst_nodes, &err };
         mp.tri_store = &tri_store;
         Tree mt;
         if (!build_tree(mp, in->next, mt)) return false;
         visited += mp.visited;
+        const auto t1 = std::chrono::steady_clock::now();
         Collapse mc(mt); mc.run(mt.root);
+        const auto t2 = std::chrono::steady_clock::now();
         Emitter em{ out, mt, &mc, false, &tri_store, nullptr, nullptr };
         mesh_roots[in->next] = em.run();
         mesh_depth = std::max(mesh_depth, em.max_depth);
+        if (getenv("IMBA_VERBOSE")) {
+            const auto t3 = std::chrono::steady_clock::now();
+            auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+            fprintf(stderr, "[imba] bvh8 mesh: %zu tree nodes; parse %.0f ms, collapse %.0f ms, emit %.0f ms\n", mt.n.size(), ms(t0, t1), ms(t1, t2), ms(t2, t3));
+        }
     }
     Collapse tc(tt); tc.run(tt.root);
     Emitter em{ out, tt, &tc, true, nullptr, &inst_store, &mesh_roots };
