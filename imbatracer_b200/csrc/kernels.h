@@ -4,7 +4,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#ifndef IMBA_TRAVERSAL_STACK
 #define IMBA_TRAVERSAL_STACK 40 /* 8-byte entries per ray; scenes needing more are rejected at upload */
+#endif
 
 struct TraceArgs {
     const uint4*   nodes;      // Node8[] as 5 x uint4

@@ -3,7 +3,10 @@ import sys, os, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import bench
-from imbatracer_b200 import api
+from imbatracer_b200 import api, abi
+import hashlib
+if os.environ.get('IMBA_LIB_VARIANT'):
+    abi.LIB_PATH = os.path.join(os.path.dirname(abi.LIB_PATH), os.environ['IMBA_LIB_VARIANT'])
 flat = bench.load_flat(); scene = api.Scene(flat); n = bench.RAYS_PER_BATCH
 cache = "/tmp/bench_batches.npz"
 if os.path.exists(cache):
@@ -22,4 +25,6 @@ for name, any_hit in bench.BATCH_ORDER:
     for _ in range(10): scene.trace(dev[name], hits, any_hit=bool(any_hit), count=n)
     e1.record(); torch.cuda.synchronize()
     res[name] = round(n * 10 / e0.elapsed_time(e1) / 1e3, 1)
-print({k: v for k, v in os.environ.items() if k.startswith("IMBA_")}, json.dumps(res), "Mrays/s total", round(4 * n / sum(n / v / 1e3 for v in res.values()) / 1e3, 1))
+    h = hits.cpu().numpy()
+    res[name + '_sha'] = hashlib.sha256((h[:, 0] >= 0).tobytes() if any_hit else h.tobytes()).hexdigest()[:12]
+print({k: v for k, v in os.environ.items() if k.startswith("IMBA_")}, json.dumps(res), "Mrays/s total", round(4 * n / sum(n / v / 1e3 for k, v in res.items() if not k.endswith('_sha')) / 1e3, 1))

@@ -9,9 +9,13 @@ python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; 
 tail -3 gpurun_out/smoke.log
 python bench.py --steps 10 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"
 cat gpurun_out/bench.json; tail -5 gpurun_out/bench.err
-if [ "$1" = "ncu" ]; then
+# at most ONE profiler pass per box session, and only after the same command exited 0 without it
+if [ "$1" = "list" ]; then
 python bench.py --steps 2 --warmup 3 > gpurun_out/plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 > gpurun_out/ncu_list.log 2>&1
+tail -3 gpurun_out/ncu_list.log
+fi
+if [ "$1" = "full" ]; then
 python bench.py --steps 2 --warmup 3 > gpurun_out/plain2.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:trace_kernel -s 24 -c 4 -o gpurun_out/prof python bench.py --steps 2 --warmup 3 > gpurun_out/ncu_full.log 2>&1
 tail -3 gpurun_out/ncu_full.log
