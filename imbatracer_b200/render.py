@@ -28,6 +28,20 @@ def rmse_like_imagemagick(a8, b8):
     return float(np.sqrt(np.mean(d * d)))
 
 
+def compare_with_reference(radiance, ref_path, gamma=0.5):
+    """RMSE of the image against a reference: a PNG (box-resized to the image size) or one of the committed
+    tests/golden/ref_*_128.npy files (linear radiance, 128x128; the image is box-filtered down to it first)."""
+    h, w, _ = radiance.shape
+    if ref_path.endswith(".npy"):
+        ref = np.load(ref_path)
+        rh, rw, _ = ref.shape
+        small = radiance[:h - h % rh, :w - w % rw].reshape(rh, h // rh, rw, w // rw, 3).mean(axis=(1, 3))
+        return rmse_like_imagemagick(to_png_array(small, gamma), to_png_array(ref, gamma))
+    from PIL import Image
+    ref = np.asarray(Image.open(ref_path).convert("RGB").resize((w, h), Image.BOX))
+    return rmse_like_imagemagick(to_png_array(radiance, gamma), ref)
+
+
 def main(argv=None):
     ap = argparse.ArgumentParser(add_help=False)
     ap.add_argument("scene"); ap.add_argument("out", nargs="?")
@@ -38,6 +52,7 @@ def main(argv=None):
     ap.add_argument("--light-path-count", type=int, default=0); ap.add_argument("-r", type=float, default=2.0)
     ap.add_argument("-c", type=int, default=1); ap.add_argument("-k", type=int, default=10); ap.add_argument("--gamma", type=float, default=0.5)
     ap.add_argument("--seed", type=int, default=1); ap.add_argument("--compare"); ap.add_argument("--help", action="help")
+    ap.add_argument("--intermediate-path"); ap.add_argument("--intermediate-time", type=float, default=10.0)
     a = ap.parse_args(argv)
     if a.s <= 0 and a.t <= 0:
         a.s = 16
@@ -59,30 +74,37 @@ def main(argv=None):
     integ.preprocess()
     loop = ProgressiveRenderer(integ, a.w, a.h, a.spp)
     t0 = time.time()
+    next_dump = a.intermediate_time
     while True:
         loop.step(1)
         samples = loop.iterations * world * a.spp
         if a.s > 0 and samples >= a.s:
             break
-        if a.t > 0:
+        if a.t > 0 or a.intermediate_path:
             integ.sync()
-            if time.time() - t0 >= a.t:
+            el = time.time() - t0
+            if a.intermediate_path and el >= next_dump:   # convergence series, render_window.cpp:72-81
+                part = loop.image().cpu().numpy()
+                if rank == 0:
+                    from PIL import Image
+                    Image.fromarray(to_png_array(part, a.gamma)).save(f"{a.intermediate_path}{int(el * 1000)}ms.png")
+                next_dump += a.intermediate_time
+            if a.t > 0 and el >= a.t:
                 break
     img = loop.image().cpu().numpy()
     secs = time.time() - t0
     if rank == 0:
         frames = loop.iterations * world
-        print(f"Done after {secs} seconds, {frames * a.spp} samples @ {frames / secs} frames per second, {1000.0 * secs / frames}ms per frame")
-        prim, shad = integ.ray_counts()
-        print(f"{prim} primary ray(s), {shad} shadow ray(s) on rank 0")
         png = to_png_array(img, a.gamma)
         if a.out:
             from PIL import Image
             Image.fromarray(png).save(a.out)
         if a.compare:
-            from PIL import Image
-            ref = np.asarray(Image.open(a.compare).convert("RGB").resize((a.w, a.h), Image.BOX))
-            print(f"RMSE {rmse_like_imagemagick(png, ref)}")
+            print(f"RMSE {compare_with_reference(img, a.compare, a.gamma)}")
+        # the two lines test/run_bench.py parses (its regexes at :170 and :203), last in the output
+        print(f"Done after {secs} seconds, {frames * a.spp} samples @ {frames / secs} frames per second, {1000.0 * secs / frames}ms per frame")
+        prim, shad = integ.ray_counts()
+        print(f"Number primary rays: {prim * world} Number shadow rays: {shad * world}")
     integ.close(); scene.close()
     if world > 1:
         dist.destroy_process_group()
