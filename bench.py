@@ -1,7 +1,9 @@
 #!/usr/bin/env python
 """bench.py -- traversal micro-bench of BASELINE.json configs[1]: 4 Mi coherent primary rays and 4 Mi incoherent
-diffuse-bounce rays, closest-hit and occlusion, per step (16 Mi rays), on the BVH of a Cornell scene (the Still Life
-geometry is not shipped with the reference; the workload name says which scene is used).
+diffuse-bounce rays, closest-hit and occlusion, per step (16 Mi rays), on the BVH of "stilllife-proxy": the Still Life
+geometry is not shipped with the reference, so the scene is a procedural stand-in with the camera of
+still_life.scene and the 23 materials of still_life.mtl (imbatracer_b200/procedural.py, ~1.5 M triangles, structure built
+by the product's host builder in the reference's BVH2 layout so that the CPU arm traces the very same tree).
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
@@ -24,14 +26,20 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 RAYS_PER_BATCH = 1 << 22
-SCENE = "cornell_water"
+SCENE = "stilllife-proxy"
 LAYOUT = "gpu"  # the reference's BVH2 ("--gpu") layout converts to the better 8-wide tree
+PROXY_DETAIL = float(os.environ.get("IMBA_BENCH_DETAIL", "1.0"))
 METRIC = "Mrays/s (closest-hit + occlusion, coherent + incoherent)"
 
 
 def load_flat():
+    from imbatracer_b200 import procedural
+    return procedural.still_life_proxy(PROXY_DETAIL, name=SCENE, accel="host")
+
+
+def load_cornell(name="cornell_water"):
     from imbatracer_b200.scene import FlatScene
-    return FlatScene.load(os.path.join(ROOT, "tests", "golden", f"scene_{SCENE}_{LAYOUT}.npz"), SCENE)
+    return FlatScene.load(os.path.join(ROOT, "tests", "golden", f"scene_{name}_{LAYOUT}.npz"), name)
 
 
 def camera_basis(flat, fov=60.0):
@@ -182,8 +190,8 @@ def run_reference(args):
 
 
 def workload_config(flat, n):
-    return {"workload": f"traversal micro-bench on the {SCENE} BVH (reference {('BVH2' if LAYOUT == 'gpu' else 'MBVH4')} layout, {flat.tri_count} triangles; "
-                        f"Still Life geometry is absent from the reference tree): per step {n} coherent primary + {n} diffuse-bounce closest-hit rays and "
+    return {"workload": f"traversal micro-bench on the {SCENE} BVH (procedural stand-in for Still Life, whose geometry is absent from the reference "
+                        f"tree: camera of still_life.scene, the 23 materials of still_life.mtl, {flat.tri_count} triangles, reference BVH2 layout): per step {n} coherent primary + {n} diffuse-bounce closest-hit rays and "
                         f"{n} + {n} shadow rays", "rays_per_step": 4 * n, "l2_policy": "inputs larger than L2 (each ray queue is 128 MiB, each hit queue 64 MiB)",
             "parallelism": "independent ray queues per GPU, no collective"}
 
@@ -226,9 +234,9 @@ def run_extra_scenes(rank):
     from imbatracer_b200 import api, procedural
     from tests import raygen
     out = {}
-    base = load_flat()
+    base = load_cornell("cornell_water")
     n = 1 << 22
-    for label, make in (("instanced_19M", lambda: procedural.instanced_grid(base, 14, 14, 14)), ("terrain_4.7M", lambda: procedural.terrain(1536))):
+    for label, make in (("cornell_water", lambda: base), ("instanced_19M", lambda: procedural.instanced_grid(base, 14, 14, 14)), ("terrain_4.7M", lambda: procedural.terrain(1536))):
         flat = make()
         scene = api.Scene(flat)
         rays = raygen.random_rays(flat, n, 11, tmax_mix=False); rays["tmin"] = 0

@@ -1,6 +1,6 @@
 """Generates the committed fixtures under tests/golden/ from the reference tree (run in the build container only):
 
-  python tests/golden/make_fixtures.py [/root/reference]
+  python tests/golden/make_fixtures.py [/root/reference [scene ...]]
 
   scene_<name>_<cpu|gpu>.npz  flattened scene exactly as the reference's loader + SBVH builder + adapters produce it
                               (frontend/build_scene.cpp:548, core/cpu_adapter.cpp, core/gpu_adapter.cpp, render/scene.cpp),
@@ -9,6 +9,8 @@
   ref_<image>_128.npy         the reference's converged golden PNGs (test/references/*.png), box-filtered to 128x128 in
                               linear radiance (PNG = 8 bit, gamma 0.5, store_png.h:59-62)
   CornellBox-*.bvh            acceleration-structure caches written by the reference's own loader (load_bvh.cpp)
+  scene_stilllife_proxy_*     the procedural Still Life stand-in (imbatracer_b200/procedural.py, detail refapi.PROXY_DETAIL) written as
+                              OBJ/MTL/TGA by tests/obj_export.py and read back through the reference's loader + SBVH builder
   rng_kat.npz                 known-answer values of the reference's RNG (render/random.h:15-47) and of the primary-ray
                               seeding (ray_gen.h:57-72), produced by the unmodified reference headers
 Also copies the reference's Cornell scenes to oracle/_ref/scenes (git-ignored scratch; the reference loader writes .bvh
@@ -25,17 +27,18 @@ sys.path.insert(0, ROOT)
 
 from tests import refapi, raygen  # noqa: E402
 
-SCENES = ["cornell_org", "cornell_indirect", "cornell_water", "cornell_instances", "cornell_specular_front"]
+SCENES = ["cornell_org", "cornell_indirect", "cornell_water", "cornell_instances", "cornell_specular_front", "stilllife_proxy"]
 IMAGES = ["cornell_org", "cornell_indirect", "cornell_specular", "cornell_specular_front", "cornell_water"]
 
 
 def main():
     ref_root = sys.argv[1] if len(sys.argv) > 1 else "/root/reference"
     scenes = refapi.ensure_ref_scenes(ref_root)
-    for name in SCENES:
+    only = sys.argv[2:]                      # optional: regenerate just these scenes
+    for name in (only or SCENES):
         flat = {}
         for gpu in (False, True):
-            rs = refapi.RefScene(f"{scenes}/cornell/{name}.scene", gpu)
+            rs = refapi.RefScene(refapi.scene_path(name), gpu)
             fs = rs.flat(name)
             fs.save(os.path.join(HERE, f"scene_{name}_{'gpu' if gpu else 'cpu'}.npz"))
             flat[gpu] = fs
@@ -54,6 +57,8 @@ def main():
         np.savez_compressed(os.path.join(HERE, f"hits_{name}.npz"), **out)
         print(name, "tris", flat[False].tri_count, "rays", len(rays))
 
+    if only:
+        return
     # .bvh caches the reference's loader wrote next to the meshes while loading (render/scene.cpp:67, loaders/load_bvh.cpp)
     import shutil
     for f in ("CornellBox-Original.bvh", "CornellBox-Specular.bvh"):

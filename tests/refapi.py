@@ -124,7 +124,29 @@ def ensure_ref_scenes(reference_root="/root/reference"):
             return None
         os.makedirs(REF_SCENES, exist_ok=True)
         shutil.copytree(src, os.path.join(REF_SCENES, "cornell"))
+    ensure_proxy_scene()
     return REF_SCENES
+
+
+PROXY_DETAIL = 0.02   # ~31 k triangles: what the parity fixtures and the reference-side harness use
+
+
+def ensure_proxy_scene():
+    """Writes the procedural Still Life stand-in (imbatracer_b200/procedural.py) as OBJ/MTL/TGA/.scene into the scratch
+    scene directory, for the reference's loader."""
+    d = os.path.join(REF_SCENES, "stilllife_proxy")
+    if not os.path.exists(os.path.join(d, "stilllife_proxy.scene")):
+        from imbatracer_b200 import procedural
+        from tests import obj_export
+        obj_export.write_scene(procedural.still_life_proxy(PROXY_DETAIL, accel=None), d)
+    return d
+
+
+def scene_path(name):
+    """.scene file of a test scene inside the scratch copy."""
+    if name == "stilllife_proxy":
+        return os.path.join(ensure_proxy_scene(), "stilllife_proxy.scene")
+    return os.path.join(REF_SCENES, "cornell", name + ".scene")
 
 
 class RefScene:

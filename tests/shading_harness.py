@@ -61,7 +61,7 @@ def run_waves(scene_name, w=96, h=96, waves=4, max_path_len=10, layout="gpu", ve
     """Wave k feeds the REFERENCE's continuation queue of wave k-1 (traced by the oracle) to both implementations."""
     from tests.conftest import load_scene
     flat = load_scene(scene_name, layout)
-    rs = refapi.RefScene(os.path.join(refapi.REF_SCENES, "cornell", scene_name + ".scene"), layout == "gpu")
+    rs = refapi.RefScene(refapi.scene_path(scene_name), layout == "gpu")
     if envmap:    # environment map + EnvLight injected on the reference side
         assert rs.add_test_envmap() == 1
         flat = rs.flat(scene_name)

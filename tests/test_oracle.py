@@ -101,7 +101,7 @@ def test_rng_known_answers():
 def test_reference_pipeline_with_oracle_reproduces_golden_image(scene, algo, image, tol):
     """The reference's own integrators (PT / BPT) running on the oracle's traversal must converge to the reference's
     golden PNG (test/render_refs.sh settings, 128x128, gamma-0.5 RMSE as test/run_bench.py:113-129 measures it)."""
-    rs = refapi.RefScene(os.path.join(refapi.REF_SCENES, "cornell", scene + ".scene"), False)
+    rs = refapi.RefScene(refapi.scene_path(scene), False)
     img, st = rs.render(algo, 128, 128, iterations=48)
     rs.close()
     got = np.clip(img / 48.0, 0, None) ** 0.5

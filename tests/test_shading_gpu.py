@@ -20,7 +20,7 @@ needs_ref = pytest.mark.skipif(not refapi.have_ref() or not os.path.isdir(refapi
 
 
 @needs_ref
-@pytest.mark.parametrize("scene", ["cornell_org", "cornell_specular_front", "cornell_water", "cornell_instances"])
+@pytest.mark.parametrize("scene", ["cornell_org", "cornell_specular_front", "cornell_water", "cornell_instances", "stilllife_proxy"])
 def test_pt_shading_stage_matches_reference_wavefronts(scene):
     from tests import shading_harness as sh
     res = sh.run_waves(scene, w=96, h=96, waves=5)
@@ -94,7 +94,7 @@ def test_device_path_tracer_converges_to_reference(scene, tol_ref):
     assert np.isfinite(img).all() and img.min() >= 0
     assert not np.array_equal(img, img2) and gamma_rmse(img, img2) < tol_ref  # two independent sample sets (caustic noise in the water scene)
     if refapi.have_ref() and os.path.isdir(refapi.REF_SCENES):
-        rs = refapi.RefScene(os.path.join(refapi.REF_SCENES, "cornell", scene + ".scene"), True)
+        rs = refapi.RefScene(refapi.scene_path(scene), True)
         ref_img, st = rs.render(0, 128, 128, iterations=64)
         rs.close()
         assert abs(st["pixel_size"] - px) < 1e-4 * px, (st["pixel_size"], px)

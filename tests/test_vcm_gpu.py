@@ -54,7 +54,7 @@ def test_algorithms_agree_with_each_other(rendered):
 @pytest.mark.parametrize("algo,tol", [("vcm_pt", 0.07), ("lt", 0.08), ("bpt", 0.05), ("ppm", 0.05), ("vcm", 0.05)])
 def test_matches_reference_integrator(rendered, algo, tol):
     img, (prim, shad) = rendered[algo]
-    rs = refapi.RefScene(os.path.join(refapi.REF_SCENES, "cornell", "cornell_org.scene"), True)
+    rs = refapi.RefScene(refapi.scene_path("cornell_org"), True)
     n = 32
     ref, st = rs.render(REF_ALGO[algo], 96, 96, iterations=n, tile=32)  # DefaultTileGen drops slivers < tile/2 (tile_gen.h:51-77)
     rs.close()
@@ -79,7 +79,7 @@ def test_vcm_needs_preprocess_and_valid_settings():
 
 
 @needs_ref
-@pytest.mark.parametrize("scene", ["cornell_org", "cornell_specular_front", "cornell_instances"])
+@pytest.mark.parametrize("scene", ["cornell_org", "cornell_specular_front", "cornell_instances", "stilllife_proxy"])
 @pytest.mark.parametrize("algo", ["vcm", "bpt", "ppm", "lt", "vcm_pt"])
 def test_vcm_stages_match_reference_wavefronts(scene, algo):
     """Stage level: the reference's own process_light_rays / process_camera_rays (vcm.cpp:193-258, 323-439) against the CUDA

@@ -57,7 +57,7 @@ def compare_keyed(ra, da, key_field, fields, tol):
 def run(scene_name, algo, w=64, h=64, waves=4, iteration=3, layout="gpu", tol=5e-4, verbose=False, envmap=False):
     from tests.conftest import load_scene
     flat = load_scene(scene_name, layout)
-    rs = refapi.RefScene(os.path.join(refapi.REF_SCENES, "cornell", scene_name + ".scene"), layout == "gpu")
+    rs = refapi.RefScene(refapi.scene_path(scene_name), layout == "gpu")
     if envmap:
         assert rs.add_test_envmap() == 1
         flat = rs.flat(scene_name)

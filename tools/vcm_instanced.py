@@ -2,7 +2,7 @@ import sys, os, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench
 from imbatracer_b200 import api, procedural
-base = bench.load_flat()
+base = bench.load_cornell()
 flat = procedural.instanced_grid(base, 14, 14, 14)
 scene = api.Scene(flat)
 for algo in sys.argv[1:] or ["pt", "lt", "bpt", "ppm", "vcm"]:
