@@ -151,6 +151,16 @@ def measured_peak_hbm():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of the incoherent closest-hit launch, from the last `ncu --set full` capture of
+    this command (tools/ncu_summary.py writes the file); None if no capture has been committed for the current workload."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if not os.path.exists(p):
+        return None
+    t = json.load(open(p))
+    return t.get("dram_bytes_per_launch") if t.get("workload") == SCENE else None
+
+
 def cpu_arm(flat, batches, sample, threads):
     """The oracle (CPU restatement of the reference's traversal entry points) on `sample` rays of every batch."""
     from tests import refapi
@@ -382,11 +392,13 @@ def run_ours(args):
                 "clocks": sampler.summary(),
                 "pt": pt, "scenes": run_extra_scenes(rank),
                 "per_kernel": {name: {"ms": per_kernel_ms[i], "mrays_s": n / per_kernel_ms[i] / 1e3} for i, (name, _) in enumerate(BATCH_ORDER)},
-                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(),
                              "kernel": "trace_kernel<closest> on the incoherent batch", "peak_source": peak_src,
                              "bytes_per_ray": bytes_per_ray, "nodes_per_ray": c[0], "tris_per_ray": c[1], "instances_per_ray": c[2],
-                             "note": "algorithmic bytes = ray 32 + hit 16 + 80/node + 48/triangle + 64/instance fetched; node and triangle fetches of this "
-                                     "0.5 MB scene are served by L1/L2, only the ray and hit queues (48 B/ray) stream from HBM"},
+                             "algorithmic_bytes_per_launch": bytes_per_ray * n, "structure_bytes": int(scene.stats()["bytes"]),
+                             "note": "algorithmic bytes = ray 32 + hit 16 + 80/node + 48/triangle + 64/instance fetched (counted by the instrumented kernel on "
+                                     "this batch); traffic = dram bytes of the same launch from the committed ncu capture (profiles/ncu_traffic.json), "
+                                     "the difference is what L1/L2 serve"},
                 "cpu_baseline": {"value": cpu_total / cpu_secs / 1e6, "unit": "Mrays/s", "cores": cores, "kind": "port",
                                  "sample": f"first {sample} rays of each of the 4 batches, oracle/traversal_oracle.cpp with {cores} threads"}}
     scene.close()

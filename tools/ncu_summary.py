@@ -1,7 +1,13 @@
 #!/usr/bin/env python
 """Summarises an .ncu-rep (ncu --set full) into a small CSV of the metrics DESIGN.md quotes.
-usage: tools/ncu_summary.py gpurun_out/prof.ncu-rep profiles/r1_trace_full.csv"""
+usage: tools/ncu_summary.py gpurun_out/prof.ncu-rep profiles/r1_trace_full.csv [workload-name]
+With a workload name (bench.py's SCENE) it also writes profiles/ncu_traffic.json: the DRAM bytes of the incoherent closest-hit
+launch, which bench.py reports as roofline.traffic.  The capture holds four consecutive trace launches of bench.py's step
+(coherent closest, incoherent closest, coherent occluded, incoherent occluded, cyclically): the incoherent closest-hit launch
+is the second of the two adjacent trace_kernel<0,...> launches."""
 import csv
+import json
+import os
 import subprocess
 import sys
 
@@ -36,6 +42,18 @@ def main():
         for name, i in cols:
             w.writerow([name, units[i]] + [r[i] for r in data])
     print(open(out).read())
+    if len(sys.argv) > 3 and len(data) == 4:
+        ki = hdr.index("Kernel Name") if "Kernel Name" in hdr else None
+        names = [r[ki] for r in data]
+        closest = ["trace_kernel<0" in x for x in names]
+        pick = [i for i in range(4) if closest[i] and closest[(i - 1) % 4]]
+        if len(pick) == 1:
+            i = pick[0]
+            val = lambda m: float(data[i][hdr.index(m)].replace(",", "")) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[units[hdr.index(m)]]
+            t = {"workload": sys.argv[3], "kernel": names[i], "dram_bytes_per_launch": val("dram__bytes_read.sum") + val("dram__bytes_write.sum"),
+                 "dram_read": val("dram__bytes_read.sum"), "dram_write": val("dram__bytes_write.sum"), "source": os.path.basename(out)}
+            json.dump(t, open(os.path.join(os.path.dirname(out), "ncu_traffic.json"), "w"), indent=1)
+            print("traffic", t)
 
 
 if __name__ == "__main__":
