@@ -26,5 +26,8 @@ for name, any_hit in bench.BATCH_ORDER:
     e1.record(); torch.cuda.synchronize()
     res[name] = round(n * 10 / e0.elapsed_time(e1) / 1e3, 1)
     h = hits.cpu().numpy()
-    res[name + '_sha'] = hashlib.sha256((h[:, 0] >= 0).tobytes() if any_hit else h.tobytes()).hexdigest()[:12]
+    cnt = torch.zeros((n, 4), dtype=torch.int32, device='cuda'); scene.trace(dev[name], hits, any_hit=bool(any_hit), count=n, counters=cnt)
+    c = cnt.double().mean(0).cpu().numpy(); res[name + '_sha'] = [round(float(c[0]), 2), round(float(c[1]), 2), int(cnt[:, 3].max())]
+    res_sha = None
+    res[name + '_sha'] = res[name + '_sha'] + [hashlib.sha256((h[:, 0] >= 0).tobytes() if any_hit else h.tobytes()).hexdigest()[:8]]
 print({k: v for k, v in os.environ.items() if k.startswith("IMBA_")}, json.dumps(res), "Mrays/s total", round(4 * n / sum(n / v / 1e3 for k, v in res.items() if not k.endswith('_sha')) / 1e3, 1))
