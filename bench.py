@@ -236,6 +236,31 @@ def run_pt(scene, flat, rank, world, barrier, dist, iters, width=1920, height=10
             "framebuffer_allreduce_bytes": width * height * 12 if dist is not None else 0, "mean_radiance": mean}
 
 
+def device_build_entry(flat, d_rays, hits, n):
+    """Row f1 end to end: imba_scene_create with IMBA_ACCEL_DEVICE_BUILD (LBVH + 8-wide collapse + emission on the device,
+    csrc/bvh8_gpu.cu) and closest-hit traversal of the same rays on the resulting tree."""
+    import torch
+    from imbatracer_b200 import api, procedural
+    api.Scene(procedural.terrain(8), device_build=True).close()   # first use loads the builder's kernels (lazy module loading): not timed
+    t0 = time.perf_counter(); sc = api.Scene(flat, device_build=True); wall = time.perf_counter() - t0
+    info, st = sc.build_info(), sc.stats()
+    cnt = torch.zeros((n, 4), dtype=torch.int32, device="cuda")
+    sc.trace(d_rays, hits, counters=cnt); torch.cuda.synchronize()
+    c = cnt.double().mean(0).cpu().numpy()
+    for _ in range(3):
+        sc.trace(d_rays, hits)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5):
+        sc.trace(d_rays, hits)
+    e1.record(); torch.cuda.synchronize()
+    out = {"build_device_ms": info["device_seconds"] * 1e3, "scene_create_call_s": wall, "mesh_levels": info["mesh_levels"], "bvh8_bytes": int(st["bytes"]),
+           "closest_mrays_s": n * 5 / e0.elapsed_time(e1) / 1e3, "nodes_per_ray": c[0], "tris_per_ray": c[1]}
+    sc.close()
+    return out
+
+
 def run_extra_scenes(rank):
     """configs[4] and a memory-bound case (rank 0 only, after the timed regions): incoherent traversal on the procedural
     ~19 M-triangle instanced scene and on a 4.7 M-triangle unique terrain (292 MB of nodes + triangles, > L2), plus VCM with
@@ -287,6 +312,7 @@ def run_extra_scenes(rank):
             e1.record(); torch.cuda.synchronize()
             r["gpu_lbvh"] = {"build_device_ms": flat.build_seconds * 1e3, "build_call_s": wall, "closest_mrays_s": n * 5 / e0.elapsed_time(e1) / 1e3}
             scene2.close()
+            r["device_build"] = device_build_entry(flat, d, hits, n)
         out[label] = r
         scene.close()
     return out
@@ -383,6 +409,8 @@ def run_ours(args):
         cores = os.cpu_count()
         sample = 1 << 20
         cpu_total, cpu_secs = cpu_arm(flat, batches, sample, cores)
+        device_build = device_build_entry(flat, dev["incoherent_closest"], hits["incoherent_closest"], n)
+        device_build["rays"] = "the incoherent closest-hit batch"
         line = {"metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic", "config": workload_config(flat, n),
@@ -390,7 +418,7 @@ def run_ours(args):
                         "steps": e2e_steps, "note": "imba_trace_host on pinned host queues, wall clock with device sync"},
                 "gpu_launches": int(launches),
                 "clocks": sampler.summary(),
-                "pt": pt, "scenes": run_extra_scenes(rank),
+                "pt": pt, "scenes": run_extra_scenes(rank), "device_build": device_build,
                 "per_kernel": {name: {"ms": per_kernel_ms[i], "mrays_s": n / per_kernel_ms[i] / 1e3} for i, (name, _) in enumerate(BATCH_ORDER)},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(),
                              "kernel": "trace_kernel<closest> on the incoherent batch", "peak_source": peak_src,

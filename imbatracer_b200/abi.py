@@ -120,6 +120,7 @@ def lib():
     L.imba_scene_create.restype = vp; L.imba_scene_create.argtypes = [C.POINTER(SceneDesc)]
     L.imba_scene_destroy.restype = None; L.imba_scene_destroy.argtypes = [vp]
     L.imba_scene_stats.argtypes = [vp, C.POINTER(i64 * 5)]
+    L.imba_scene_build_info.argtypes = [vp, C.POINTER(C.c_float * 2)]
     L.imba_trace.argtypes = [vp, vp, vp, i32, i32, vp, vp]
     L.imba_trace_host.argtypes = [vp, vp, vp, i32, i32]
     L.imba_host_register.argtypes = [vp, C.c_size_t]

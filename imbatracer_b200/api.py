@@ -17,10 +17,15 @@ def _stream_ptr(stream=None):
 class Scene:
     """imba_scene: the flattened scene on the current CUDA device with the compressed 8-wide BVH."""
 
-    def __init__(self, flat: FlatScene):
+    def __init__(self, flat: FlatScene, device_build=False):
+        """device_build: ignore any acceleration structure in `flat` and build it on the device from the meshes and
+        instances (IMBA_ACCEL_DEVICE_BUILD: linear BVH + 8-wide collapse, csrc/bvh8_gpu.cu)."""
         self.L = abi.lib()
         self.flat = flat
         d = flat.desc()
+        if device_build:
+            d.accel_layout = 2; d.nodes = None; d.tris = None; d.inst_nodes = None
+            d.node_count = 0; d.tri_vec4_count = 0; d.inst_node_count = 0
         self.h = self.L.imba_scene_create(C.byref(d))
         if not self.h:
             raise RuntimeError("imba_scene_create failed: " + abi.last_error())
@@ -39,6 +44,11 @@ class Scene:
         out = (C.c_int64 * 5)()
         abi.check(self.L.imba_scene_stats(self.h, C.byref(out)), "imba_scene_stats")
         return {"nodes": out[0], "triangles": out[1], "instances": out[2], "bytes": out[3], "max_depth": out[4]}
+
+    def build_info(self):
+        out = (C.c_float * 2)()
+        abi.check(self.L.imba_scene_build_info(self.h, C.byref(out)), "imba_scene_build_info")
+        return {"device_seconds": out[0], "mesh_levels": int(out[1])}
 
     def trace(self, rays, hits=None, any_hit=False, counters=None, count=None, stream=None):
         """rays: CUDA uint8/float32 tensor holding imba_ray[count]; returns the hits tensor (int32 [count, 4])."""

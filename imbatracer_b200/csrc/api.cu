@@ -61,11 +61,15 @@ extern "C" imba_scene* imba_scene_create(const imba_scene_desc* d) {
     if (!d) { imba_set_error("null scene description"); return nullptr; }
     imba_scene* s = new imba_scene;
     if (init_device(s) != IMBA_OK) { delete s; return nullptr; }
-    Bvh8 b; std::string err;
-    if (!imba_build_bvh8(d->accel_layout, d->root, d->nodes, d->tris, d->inst_nodes, b, err)) {
-        imba_set_error("BVH conversion failed: %s", err.c_str()); delete s; return nullptr;
+    if (d->accel_layout == IMBA_ACCEL_DEVICE_BUILD) { // no reference-built structure: LBVH + 8-wide collapse on the device
+        if (imba_scene_build_accel_device(s, d, s->build_info) != IMBA_OK) { imba_scene_destroy(s); return nullptr; }
+    } else {
+        Bvh8 b; std::string err;
+        if (!imba_build_bvh8(d->accel_layout, d->root, d->nodes, d->tris, d->inst_nodes, b, err)) {
+            imba_set_error("BVH conversion failed: %s", err.c_str()); delete s; return nullptr;
+        }
+        if (imba_scene_upload_accel(s, b) != IMBA_OK) { imba_scene_destroy(s); return nullptr; }
     }
-    if (imba_scene_upload_accel(s, b) != IMBA_OK) { imba_scene_destroy(s); return nullptr; }
     // opacity masks: active only if some descriptor is not the always-opaque (1,1,0) (core/mask.h:14-26)
     for (int i = 0; i < d->mask_count; ++i)
         if (!(d->masks[i].width == 1 && d->masks[i].height == 1 && d->masks[i].offset == 0)) s->has_masks = true;
@@ -91,6 +95,12 @@ extern "C" void imba_scene_destroy(imba_scene* s) {
     }
     imba_shading_free(s);
     delete s;
+}
+
+extern "C" int imba_scene_build_info(const imba_scene* s, float out[2]) {
+    if (!s || !out) { imba_set_error("null argument"); return IMBA_ERR_INVALID; }
+    out[0] = s->build_info[0]; out[1] = s->build_info[1];
+    return IMBA_OK;
 }
 
 extern "C" int imba_scene_stats(const imba_scene* s, int64_t out[5]) {

@@ -28,6 +28,7 @@ struct imba_scene {
     uint4*    d_nodes = nullptr; float4* d_tris = nullptr; float4* d_insts = nullptr;
     uint32_t  top_root = 0; int flat_inst = -1;
     int64_t   stats[5] = { 0, 0, 0, 0, 0 };
+    float     build_info[2] = { 0.0f, 0.0f }; // device build: seconds of device time, levels of the deepest mesh tree
     // opacity masks
     bool      has_masks = false; bool owns_masks = true;
     int*      d_mask_indices = nullptr; float2* d_mask_texcoords = nullptr; int* d_masks = nullptr; uint8_t* d_mask_buffer = nullptr;
@@ -46,6 +47,8 @@ struct imba_scene {
 
 /* Uploads a converted structure; fills scene->d_nodes etc. */
 int imba_scene_upload_accel(imba_scene* s, const Bvh8& b);
+/* Builds the structure on the device from meshes + instances (bvh8_gpu.cu). */
+int imba_scene_build_accel_device(imba_scene* s, const imba_scene_desc* d, float* seconds);
 /* Launches traversal on device buffers. */
 struct TraceRequest {
     const imba_ray* d_rays = nullptr; imba_hit* d_hits = nullptr;

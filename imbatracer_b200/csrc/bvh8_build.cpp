@@ -320,6 +320,7 @@ struct Emitter {
     const std::vector<Tri48>* tri_store; const std::vector<const imba_instance_node*>* inst_store;
     const std::map<int, uint32_t>* mesh_roots; // reference root index -> Node8 index (top level only)
     int max_depth = 0;
+    uint32_t node_offset = 0; // Node8 index of out.nodes[0] in the final device array (device-built mesh trees come first)
 
     size_t prim_out_size() const { return top_level ? out.insts.size() : out.tris.size(); }
     void emit_prim(int store_idx) {
@@ -333,7 +334,7 @@ struct Emitter {
     struct Work { int tn; uint32_t idx; int depth; };
 
     uint32_t run() {
-        const uint32_t root_idx = (uint32_t)out.nodes.size();
+        const uint32_t root_idx = node_offset + (uint32_t)out.nodes.size();
         out.nodes.emplace_back();
         std::vector<Work> q; q.push_back({ t.root, root_idx, 1 });
         for (size_t qi = 0; qi < q.size(); ++qi) {
@@ -390,7 +391,7 @@ struct Emitter {
             }
             // children
             int n_inner = 0; for (int s = 0; s < 8; ++s) if (child_in_slot[s] >= 0 && t.n[child_in_slot[s]].nkids > 0) ++n_inner;
-            nd.child_base = (uint32_t)out.nodes.size();
+            nd.child_base = node_offset + (uint32_t)out.nodes.size();
             out.nodes.resize(out.nodes.size() + n_inner);
             nd.prim_base = (uint32_t)prim_out_size();
             int inner_rank = 0, prim_off = 0;
@@ -425,7 +426,7 @@ struct Emitter {
                     prim_off += std::min(cnt, 3);
                 }
             }
-            out.nodes[w.idx] = nd;
+            out.nodes[w.idx - node_offset] = nd;
         }
         return root_idx;
     }
@@ -487,5 +488,31 @@ bool imba_build_bvh8(int layout, int root, const void* nodes, const imba_vec4* t
     }
     // one padding triangle so that 3-wide speculative loads past the last leaf stay in bounds
     Tri48 pad; memset(&pad, 0, sizeof(pad)); pad.id = (int32_t)0x80000000; out.tris.push_back(pad);
+    return true;
+}
+
+/* Top level only: the mesh trees already exist (built on the device, bvh8_gpu.cu).  `mesh_roots` maps InstanceNode::next to the
+ * Node8 index of that mesh's root; the top-level nodes produced here will be stored from index `node_offset` on. */
+bool imba_build_bvh8_top(int layout, int root, const void* nodes, const imba_instance_node* inst_nodes,
+                         const std::map<int, uint32_t>& mesh_roots, uint32_t node_offset, Bvh8& out, std::string& err) {
+    out = Bvh8();
+    if (layout != IMBA_ACCEL_MBVH4 && layout != IMBA_ACCEL_BVH2) { err = "unknown accel layout"; return false; }
+    if (!nodes || !inst_nodes) { err = "null acceleration structure pointer"; return false; }
+    std::vector<const imba_instance_node*> inst_store;
+    Parser top{ layout, nodes, nullptr, inst_nodes, &err };
+    top.top_level = true; top.inst_store = &inst_store;
+    Tree tt;
+    if (!build_tree(top, root, tt)) return false;
+    for (const imba_instance_node* in : inst_store) if (!mesh_roots.count(in->next)) { err = "instance refers to an unknown mesh"; return false; }
+    Collapse tc(tt); tc.run(tt.root);
+    Emitter em{ out, tt, &tc, true, nullptr, &inst_store, &mesh_roots };
+    em.node_offset = node_offset;
+    out.top_root = em.run();
+    out.max_depth = em.max_depth;
+    out.ref_node_count = top.visited;
+    if (out.insts.size() == 1) {
+        static const float ident[12] = { 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0 };
+        if (memcmp(out.insts[0].m, ident, sizeof(ident)) == 0) { out.flat = true; out.flat_root = (uint32_t)out.insts[0].root; out.flat_inst = out.insts[0].inst_id; }
+    }
     return true;
 }

@@ -1,6 +1,7 @@
 /* bvh8_build.h -- host conversion of the reference's acceleration structures to the device layout (bvh8.h). */
 #ifndef IMBA_BVH8_BUILD_H
 #define IMBA_BVH8_BUILD_H
+#include <map>
 #include <string>
 #include <vector>
 #include "bvh8.h"
@@ -22,5 +23,9 @@ struct Bvh8 {
  * pointers.  Returns false and sets err on malformed input (the reference has no such check: it asserts). */
 bool imba_build_bvh8(int layout, int root, const void* nodes, const imba_vec4* tris,
                      const imba_instance_node* inst_nodes, Bvh8& out, std::string& err);
+
+/* Top level only (the mesh trees were built on the device): see bvh8_build.cpp. */
+bool imba_build_bvh8_top(int layout, int root, const void* nodes, const imba_instance_node* inst_nodes,
+                         const std::map<int, uint32_t>& mesh_roots, uint32_t node_offset, Bvh8& out, std::string& err);
 
 #endif

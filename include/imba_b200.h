@@ -96,7 +96,11 @@ void imba_l1_invalidate(void);
 /* ------------------------------------------------------------------------------------------
  * L2: flattened scene (what render/scene.h keeps host-side for shading)
  * ---------------------------------------------------------------------------------------- */
-typedef enum { IMBA_ACCEL_MBVH4 = 0, IMBA_ACCEL_BVH2 = 1 } imba_accel_layout;
+typedef enum { IMBA_ACCEL_MBVH4 = 0, IMBA_ACCEL_BVH2 = 1,
+               /* no reference-built structure is supplied (nodes / tris / inst_nodes are ignored): imba_scene_create builds the
+                * per-mesh trees on the device (linear BVH + SAH-optimal 8-wide collapse) and the small top level on the host;
+                * replaces SplitBvhBuilder (core/sbvh_builder.h) + the adapters for scenes loaded without one */
+               IMBA_ACCEL_DEVICE_BUILD = 2 } imba_accel_layout;
 typedef enum { IMBA_MAT_DIFFUSE = 0, IMBA_MAT_MIRROR = 1, IMBA_MAT_GLASS = 2, IMBA_MAT_GLOSSY = 3 } imba_material_kind;
 typedef enum { IMBA_LIGHT_TRIANGLE = 0, IMBA_LIGHT_DIRECTIONAL = 1, IMBA_LIGHT_POINT = 2, IMBA_LIGHT_SPOT = 3,
                IMBA_LIGHT_ENV = 4 } imba_light_kind;
@@ -187,6 +191,9 @@ void        imba_scene_destroy(imba_scene* scene);
 /* Statistics of the converted structure: out[0]=bvh8 nodes, [1]=triangles (48-byte blocks), [2]=instances,
  * [3]=bytes of node+triangle storage, [4]=max depth. */
 int imba_scene_stats(const imba_scene* scene, int64_t out[5]);
+/* IMBA_ACCEL_DEVICE_BUILD scenes: out[0] = device seconds of the mesh builds (sort, hierarchy, refit, collapse, emission),
+ * out[1] = levels of the deepest 8-wide mesh tree; zeros for converted scenes. */
+int imba_scene_build_info(const imba_scene* scene, float out[2]);
 
 /* Closest-hit (any_hit = 0) or occlusion (any_hit = 1) traversal of `count` rays.
  * d_rays / d_hits are device pointers; asynchronous on `stream` (a cudaStream_t, NULL = default stream).
