@@ -174,6 +174,44 @@ def cpu_arm(flat, batches, sample, threads):
     return total, secs
 
 
+CFG0 = {"width": 512, "height": 512, "spp": 16, "max_path_len": 22, "tile": 256}   # BASELINE.json configs[0]; path length as test/run_bench.py:75
+
+
+def reference_cfg0(cores):
+    """configs[0] on the host: the reference's OWN PathTracer + TileScheduler + ray queues (unmodified sources compiled into
+    oracle/_ref/libimba_ref.so, TBB shimmed onto std::thread) with the restated CPU traversal behind its four entry points, on
+    the detail-0.02 stilllife-proxy scene loaded by the reference's own OBJ loader and SBVH builder (MBVH4, its --cpu path)."""
+    from tests import refapi
+    if not refapi.have_ref():
+        return {"unavailable": "oracle/_ref/libimba_ref.so not built"}
+    rs = refapi.RefScene(refapi.scene_path("stilllife_proxy"), False)
+    rs.render(0, CFG0["width"], CFG0["height"], spp=1, iterations=1, threads=cores, tile=CFG0["tile"], max_path_len=CFG0["max_path_len"])
+    img, st = rs.render(0, CFG0["width"], CFG0["height"], spp=1, iterations=CFG0["spp"], threads=cores, tile=CFG0["tile"], max_path_len=CFG0["max_path_len"])
+    rs.close()
+    n = CFG0["width"] * CFG0["height"] * CFG0["spp"]
+    return {"workload": "PT 512x512, 16 spp, max path length 22, tile 256, stilllife-proxy at detail 0.02 (31 k triangles) through the reference's loader",
+            "samples_per_s": n / st["seconds"], "seconds": st["seconds"], "mrays_s": (st["primary_rays"] + st["shadow_rays"]) / st["seconds"] / 1e6,
+            "threads": cores, "mean_radiance": float(img.mean()) / CFG0["spp"], "kind": "reference host pipeline + restated traversal"}
+
+
+def ours_cfg0():
+    """The same configuration on the device integrator, on the same scene (the fixture the reference's loader exported)."""
+    import torch
+    from imbatracer_b200 import api
+    from imbatracer_b200.scene import FlatScene
+    flat = FlatScene.load(os.path.join(ROOT, "tests", "golden", "scene_stilllife_proxy_gpu.npz"), "stilllife_proxy")
+    sc = api.Scene(flat)
+    it = api.Integrator(sc, api.render_settings(flat, "pt", CFG0["width"], CFG0["height"], spp=1, max_path_len=CFG0["max_path_len"], seed=7))
+    it.preprocess(); it.render(2); it.sync(); it.clear()
+    t0 = time.perf_counter(); it.render(CFG0["spp"]); it.sync(); dt = time.perf_counter() - t0
+    img = it.download()
+    prim, shad = it.ray_counts()
+    it.close(); sc.close()
+    n = CFG0["width"] * CFG0["height"] * CFG0["spp"]
+    return {"workload": "PT 512x512, 16 spp, max path length 22, stilllife-proxy at detail 0.02 (31 k triangles), same scene arrays as the reference arm",
+            "samples_per_s": n / dt, "seconds": dt, "mean_radiance": float(img.mean()) / CFG0["spp"]}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -190,7 +228,8 @@ def run_reference(args):
     for _ in range(args.steps):
         a, b = cpu_arm(flat, batches, n, cores); total += a; secs += b
     v = total / secs / 1e6
-    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+    cfg0 = reference_cfg0(cores)
+    line = {"impl": "reference", "cfg0": cfg0, "metric": METRIC, "value": v, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": secs / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": workload_config(flat, n),
             "cpu_baseline": {"value": v, "unit": "Mrays/s", "cores": cores, "kind": "port",
@@ -418,7 +457,7 @@ def run_ours(args):
                         "steps": e2e_steps, "note": "imba_trace_host on pinned host queues, wall clock with device sync"},
                 "gpu_launches": int(launches),
                 "clocks": sampler.summary(),
-                "pt": pt, "scenes": run_extra_scenes(rank), "device_build": device_build,
+                "pt": pt, "cfg0": ours_cfg0(), "scenes": run_extra_scenes(rank), "device_build": device_build,
                 "per_kernel": {name: {"ms": per_kernel_ms[i], "mrays_s": n / per_kernel_ms[i] / 1e3} for i, (name, _) in enumerate(BATCH_ORDER)},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(),
                              "kernel": "trace_kernel<closest> on the incoherent batch", "peak_source": peak_src,

@@ -74,7 +74,7 @@ def gamma_rmse(a, b):
     return float(np.sqrt(np.mean((np.clip(a, 0, 1) ** 0.5 - np.clip(b, 0, 1) ** 0.5) ** 2)))
 
 
-@pytest.mark.parametrize("scene,tol_ref", [("cornell_org", 0.05), ("cornell_water", 0.16)])
+@pytest.mark.parametrize("scene,tol_ref", [("cornell_org", 0.05), ("cornell_water", 0.16), ("stilllife_proxy", 0.2)])
 def test_device_path_tracer_converges_to_reference(scene, tol_ref):
     from imbatracer_b200 import api
     flat = load_scene(scene, "gpu")
