@@ -2,7 +2,8 @@
  * "GPU BVH build (LBVH + 8-wide collapse)" replacing the host SplitBvhBuilder, core/sbvh_builder.h, and the host converter for
  * scenes that come without a reference-built structure).
  *
- *   1. binary tree per mesh on the device (lbvh.cuh: Morton codes, radix sort, Karras hierarchy, refit);
+ *   1. binary tree per mesh on the device (lbvh.cuh): Morton codes and radix sort, then parallel locally-ordered clustering
+ *      (PLOC, the default) or the Karras hierarchy + refit (IMBA_GPU_BUILDER=lbvh);
  *   2. collapse_cost_kernel: the SAH-optimal 8-wide collapse of Ylitie, Karras, Laine 2017 (section 3) as a bottom-up dynamic
  *      program -- the same recurrences as the host converter (bvh8_build.cpp: Collapse::run), one thread climbing from every
  *      leaf, the second thread to arrive at a node computes it (one atomic flag per node);
@@ -247,6 +248,7 @@ int imba_scene_build_accel_device(imba_scene* s, const imba_scene_desc* d, float
     if (d->mesh_count <= 0 || !d->mesh_vertex_base || !d->mesh_tri_base || !d->vertices || !d->indices || d->instance_count <= 0 || !d->instances) {
         imba_set_error("device build needs meshes (vertices, indices, bases) and instances"); return IMBA_ERR_INVALID;
     }
+    const bool use_ploc = !(getenv("IMBA_GPU_BUILDER") && !strcmp(getenv("IMBA_GPU_BUILDER"), "lbvh")); // default: PLOC
     const float cost_prim = getenv("IMBA_COST_PRIM") ? (float)atof(getenv("IMBA_COST_PRIM")) : 0.5f;
     const int nv = d->mesh_vertex_base[d->mesh_count], nt_all = d->mesh_tri_base[d->mesh_count];
     size_t node_cap = 0;
@@ -275,14 +277,14 @@ int imba_scene_build_accel_device(imba_scene* s, const imba_scene_desc* d, float
         BG_CUDA(F.alloc((size_t)(2 * n) * 7 * 4)); BG_CUDA(dec.alloc((size_t)n * 4)); BG_CUDA(ptot.alloc((size_t)2 * n)); BG_CUDA(flags2.alloc((size_t)n * 4));
         BG_CUDA(cudaMemset(flags2.p, 0, (size_t)n * 4));
         cudaEventRecord(e0);
-        BG_CUDA(lbvh_build_tree(m, t));
+        BG_CUDA(use_ploc ? ploc_build_tree(m, t) : lbvh_build_tree(m, t));
         CostTables T{ F.as<float>(), dec.as<uint32_t>(), ptot.as<uint8_t>() };
         const int blocks = (n + 255) / 256;
         collapse_cost_kernel<<<blocks, 256>>>(n, t.kids(), t.parents(), t.bounds(), flags2.as<int>(), T, cost_prim);
         g_imba_launches.fetch_add(1);
         // breadth-first emission; the root of this mesh is Node8 `root_idx`
         const unsigned root_idx = node_count;
-        const int root_node = 0; // the root of the binary tree; for n == 1 the only leaf has id n-1 = 0 as well
+        const int root_node = t.root; // the root of the binary tree; for n == 1 the only leaf has id n-1 = 0 as well
         BG_CUDA(cudaMemcpy(d_work.as<int>() + root_idx, &root_node, 4, cudaMemcpyHostToDevice));
         node_count = root_idx + 1;
         BG_CUDA(cudaMemcpy(ctr, &node_count, 4, cudaMemcpyHostToDevice));
@@ -303,7 +305,7 @@ int imba_scene_build_accel_device(imba_scene* s, const imba_scene_desc* d, float
         BG_CUDA(cudaEventSynchronize(e1));
         float ms = 0.0f; cudaEventElapsedTime(&ms, e0, e1); device_ms += ms;
         mesh_depth = std::max(mesh_depth, levels);
-        Box6 root; BG_CUDA(cudaMemcpy(&root, t.bounds(), sizeof(Box6), cudaMemcpyDeviceToHost));
+        Box6 root; BG_CUDA(cudaMemcpy(&root, t.bounds() + t.root, sizeof(Box6), cudaMemcpyDeviceToHost));
         memcpy(&mesh_box[6 * mi], root.v, 24);
         mesh_key[mi] = mi; mesh_roots[mi] = root_idx;
     }

@@ -48,6 +48,7 @@ extern "C" imba_accel* imba_accel_build_gpu(const imba_scene_desc* d, float* out
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { imba_set_error("no CUDA device (this library has no CPU path)"); return nullptr; }
     imba_accel* out = new imba_accel;
+    const bool use_ploc = getenv("IMBA_GPU_BUILDER") && !strcmp(getenv("IMBA_GPU_BUILDER"), "ploc"); // default here: the Karras hierarchy
     const int nv = d->mesh_vertex_base[d->mesh_count], nt_all = d->mesh_tri_base[d->mesh_count];
     DeviceBuf d_vertices, d_indices;
     LB_CUDA(d_vertices.alloc((size_t)nv * 16)); LB_CUDA(d_indices.alloc((size_t)nt_all * 16));
@@ -65,7 +66,7 @@ extern "C" imba_accel* imba_accel_build_gpu(const imba_scene_desc* d, float* out
         LB_CUDA(d_nodes.alloc((size_t)std::max(n - 1, 1) * sizeof(imba_node2))); LB_CUDA(d_tris.alloc((size_t)n * 48));
         const int blocks = (n + 255) / 256;
         cudaEventRecord(e0);
-        LB_CUDA(lbvh_build_tree(m, t));
+        LB_CUDA(use_ploc ? ploc_build_tree(m, t) : lbvh_build_tree(m, t));
         lbvh_emit_kernel<<<blocks, 256>>>(m, t.sorted_ids(), n, t.kids(), t.bounds(), node_base, vec4_base, d_nodes.as<imba_node2>(), d_tris.as<float4>());
         cudaEventRecord(e1);
         LB_CUDA(cudaGetLastError());
@@ -78,7 +79,7 @@ extern "C" imba_accel* imba_accel_build_gpu(const imba_scene_desc* d, float* out
             out->nodes.resize((size_t)node_base + n - 1);
             LB_CUDA(cudaMemcpy(out->nodes.data() + node_base, d_nodes.p, (size_t)(n - 1) * sizeof(imba_node2), cudaMemcpyDeviceToHost));
             Box6 root;
-            LB_CUDA(cudaMemcpy(&root, t.bounds(), sizeof(Box6), cudaMemcpyDeviceToHost));
+            LB_CUDA(cudaMemcpy(&root, t.bounds() + t.root, sizeof(Box6), cudaMemcpyDeviceToHost));
             memcpy(&mesh_box[6 * mi], root.v, 24);
         } else { // single triangle: dummy parent (gpu_adapter.cpp:14-31)
             imba_node2 nd; memset(&nd, 0, sizeof(nd));
@@ -91,7 +92,7 @@ extern "C" imba_accel* imba_accel_build_gpu(const imba_scene_desc* d, float* out
             out->nodes.push_back(nd);
             for (int a = 0; a < 3; ++a) { mesh_box[6 * mi + a] = lo[a]; mesh_box[6 * mi + 3 + a] = hi[a]; }
         }
-        mesh_root[mi] = node_base;
+        mesh_root[mi] = node_base + t.root;
     }
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     if (imba_accel_finish_top(out, d, mesh_root.data(), mesh_box.data()) != IMBA_OK) { delete out; return nullptr; }

@@ -6,6 +6,7 @@
 #define IMBA_LBVH_CUH
 #include <cfloat>
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_select.cuh>
 #include "api_common.h"
 
 namespace {
@@ -125,6 +126,7 @@ struct DeviceBuf {
 
 struct LbvhTree {
     int n = 0;
+    int root = 0;   // id of the root among the internal nodes (0 for the Karras hierarchy; the last merge for PLOC)
     DeviceBuf bbox, keys, keys2, ids, ids2, children, parent, flags, boxes, temp;
     const int*  sorted_ids() { return ids2.as<int>(); }
     const int2* kids() { return children.as<int2>(); }
@@ -155,6 +157,106 @@ inline cudaError_t lbvh_build_tree(const MeshView& m, LbvhTree& t) {
     lbvh_refit_kernel<<<blocks, 256>>>(m, t.ids2.as<int>(), n, t.children.as<int2>(), t.parent.as<int>(), t.flags.as<int>(), t.boxes.as<Box6>());
 #undef LBT
     g_imba_launches.fetch_add(n > 1 ? 5 : 4);
+    return cudaGetLastError();
+}
+
+
+/* ---- PLOC: parallel locally-ordered clustering (Meister & Bittner 2018) ------------------------------------------------------
+ * Bottom-up agglomeration over the Morton-sorted clusters: every cluster looks for the neighbour within PLOC_RADIUS positions
+ * whose union box has the smallest area; mutual nearest neighbours merge; the cluster array is compacted; repeat until one
+ * cluster is left.  Same outputs as the Karras hierarchy (children / parent / boxes, leaves n-1+p), trees close to a
+ * binned-SAH build instead of a pure Morton split. */
+constexpr int PLOC_RADIUS = 16;
+
+__global__ void ploc_leaf_kernel(MeshView m, const int* ids, int n, Box6* boxes, int* cid) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    float4 a, b, c; tri_verts(m, ids[p], a, b, c);
+    Box6 bx;
+    bx.v[0] = fminf(a.x, fminf(b.x, c.x)); bx.v[1] = fminf(a.y, fminf(b.y, c.y)); bx.v[2] = fminf(a.z, fminf(b.z, c.z));
+    bx.v[3] = fmaxf(a.x, fmaxf(b.x, c.x)); bx.v[4] = fmaxf(a.y, fmaxf(b.y, c.y)); bx.v[5] = fmaxf(a.z, fmaxf(b.z, c.z));
+    boxes[(n - 1) + p] = bx; cid[p] = (n - 1) + p;
+}
+
+__global__ void ploc_nearest_kernel(const int* cid, int count, const Box6* boxes, int* nearest) {
+    __shared__ Box6 tile[256 + 2 * PLOC_RADIUS];
+    const int base = blockIdx.x * blockDim.x - PLOC_RADIUS;
+    for (int k = threadIdx.x; k < 256 + 2 * PLOC_RADIUS; k += blockDim.x) {
+        const int j = base + k;
+        if (j >= 0 && j < count) tile[k] = boxes[cid[j]];
+    }
+    __syncthreads();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const Box6 me = tile[threadIdx.x + PLOC_RADIUS];
+    float best = FLT_MAX; int bj = -1;
+    for (int o = -PLOC_RADIUS; o <= PLOC_RADIUS; ++o) {
+        const int j = i + o;
+        if (o == 0 || j < 0 || j >= count) continue;
+        const Box6& ot = tile[threadIdx.x + PLOC_RADIUS + o];
+        const float dx = fmaxf(me.v[3], ot.v[3]) - fminf(me.v[0], ot.v[0]), dy = fmaxf(me.v[4], ot.v[4]) - fminf(me.v[1], ot.v[1]),
+                    dz = fmaxf(me.v[5], ot.v[5]) - fminf(me.v[2], ot.v[2]);
+        const float d = dx * dy + dy * dz + dz * dx;
+        if (d < best) { best = d; bj = j; }   // ties: the lower index wins (o ascends), which guarantees a mutual pair exists
+    }
+    nearest[i] = bj;
+}
+
+__global__ void ploc_merge_kernel(const int* cid, int count, const int* nearest, Box6* boxes, int2* children, int* parent, int* next_id, int* out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const int j = nearest[i];
+    if (j < 0 || nearest[j] != i) { out[i] = cid[i]; return; }
+    if (i > j) { out[i] = -1; return; }
+    const int id = atomicAdd(next_id, 1);
+    const int a = cid[i], b = cid[j];
+    const Box6 ba = boxes[a], bb = boxes[b];
+    Box6 u;
+    for (int k = 0; k < 3; ++k) { u.v[k] = fminf(ba.v[k], bb.v[k]); u.v[3 + k] = fmaxf(ba.v[3 + k], bb.v[3 + k]); }
+    boxes[id] = u; children[id] = make_int2(a, b); parent[a] = id; parent[b] = id;
+    out[i] = id;
+}
+
+struct PlocValid { __device__ __forceinline__ bool operator()(const int& x) const { return x >= 0; } };
+
+/* Same contract as lbvh_build_tree; t.root is the id of the last merge. */
+inline cudaError_t ploc_build_tree(const MeshView& m, LbvhTree& t) {
+    const int n = m.nt; t.n = n;
+    cudaError_t e;
+#define LBT(x) do { if ((e = (x)) != cudaSuccess) return e; } while (0)
+    LBT(t.bbox.alloc(32)); LBT(t.keys.alloc((size_t)n * 8)); LBT(t.keys2.alloc((size_t)n * 8)); LBT(t.ids.alloc((size_t)n * 4)); LBT(t.ids2.alloc((size_t)n * 4));
+    LBT(t.children.alloc((size_t)n * 8)); LBT(t.parent.alloc((size_t)(2 * n) * 4)); LBT(t.flags.alloc((size_t)n * 4)); LBT(t.boxes.alloc((size_t)(2 * n) * sizeof(Box6)));
+    DeviceBuf cidA, cidB, nearest, counters;
+    LBT(cidA.alloc((size_t)n * 4)); LBT(cidB.alloc((size_t)n * 4)); LBT(nearest.alloc((size_t)n * 4)); LBT(counters.alloc(16));
+    size_t sort_bytes = 0, select_bytes = 0;
+    LBT(cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, t.keys.as<unsigned long long>(), t.keys2.as<unsigned long long>(), t.ids.as<int>(), t.ids2.as<int>(), n, 0, 63));
+    LBT(cub::DeviceSelect::If(nullptr, select_bytes, cidB.as<int>(), cidA.as<int>(), counters.as<int>() + 1, n, PlocValid()));
+    LBT(t.temp.alloc(sort_bytes > select_bytes ? sort_bytes : select_bytes));
+    size_t temp_bytes = sort_bytes > select_bytes ? sort_bytes : select_bytes;
+    static const int init_bbox[6] = { 0x7f7fffff, 0x7f7fffff, 0x7f7fffff, (int)0x80800000u, (int)0x80800000u, (int)0x80800000u };
+    LBT(cudaMemcpy(t.bbox.p, init_bbox, sizeof(init_bbox), cudaMemcpyHostToDevice));
+    LBT(cudaMemset(counters.p, 0, 16));
+    LBT(cudaMemset(t.parent.p, 0xff, (size_t)(2 * n) * 4));
+    const int blocks = (n + 255) / 256;
+    lbvh_bounds_kernel<<<blocks, 256>>>(m, t.bbox.as<int>());
+    lbvh_morton_kernel<<<blocks, 256>>>(m, t.bbox.as<int>(), t.keys.as<unsigned long long>(), t.ids.as<int>());
+    LBT(cub::DeviceRadixSort::SortPairs(t.temp.p, temp_bytes, t.keys.as<unsigned long long>(), t.keys2.as<unsigned long long>(), t.ids.as<int>(), t.ids2.as<int>(), n, 0, 63));
+    ploc_leaf_kernel<<<blocks, 256>>>(m, t.ids2.as<int>(), n, t.boxes.as<Box6>(), cidA.as<int>());
+    int launches = 4, count = n;
+    while (count > 1) {
+        const int b = (count + 255) / 256;
+        ploc_nearest_kernel<<<b, 256>>>(cidA.as<int>(), count, t.boxes.as<Box6>(), nearest.as<int>());
+        ploc_merge_kernel<<<b, 256>>>(cidA.as<int>(), count, nearest.as<int>(), t.boxes.as<Box6>(), t.children.as<int2>(), t.parent.as<int>(), counters.as<int>(), cidB.as<int>());
+        LBT(cub::DeviceSelect::If(t.temp.p, temp_bytes, cidB.as<int>(), cidA.as<int>(), counters.as<int>() + 1, count, PlocValid()));
+        int c2[2];
+        LBT(cudaMemcpy(c2, counters.p, 8, cudaMemcpyDeviceToHost));
+        if (c2[1] >= count || c2[1] < 1) return cudaErrorUnknown;   // every round merges at least one pair
+        count = c2[1]; launches += 3;
+        if (count == 1) t.root = c2[0] - 1;
+    }
+    if (n == 1) t.root = 0;
+#undef LBT
+    g_imba_launches.fetch_add(launches);
     return cudaGetLastError();
 }
 

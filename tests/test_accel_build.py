@@ -126,12 +126,14 @@ def _tiny_two_mesh_scene():
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("builder", ["ploc", "lbvh"])
 @pytest.mark.parametrize("name", ["instanced", "terrain", "proxy", "one_triangle"])
-def test_device_built_structure_gives_identical_traversal_results(scenes, name):
+def test_device_built_structure_gives_identical_traversal_results(scenes, name, builder, monkeypatch):
     """csrc/bvh8_gpu.cu (IMBA_ACCEL_DEVICE_BUILD): linear BVH + SAH-optimal 8-wide collapse + emission, all on the device,
     straight from the meshes.  A different tree again; hits must equal the oracle's on the host-built reference-layout tree."""
     import torch
     from imbatracer_b200 import api
+    monkeypatch.setenv("IMBA_GPU_BUILDER", builder)     # binary tree: parallel locally-ordered clustering (default) or Karras LBVH
     if name == "proxy":
         s = procedural.still_life_proxy(0.02)
     elif name == "one_triangle":   # degenerate mesh sizes: a single-triangle mesh instanced twice next to a two-triangle mesh
