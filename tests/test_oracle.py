@@ -108,3 +108,26 @@ def test_reference_pipeline_with_oracle_reproduces_golden_image(scene, algo, ima
     want = np.load(os.path.join(GOLDEN, f"ref_{image}_128.npy")) ** 0.5
     rmse = float(np.sqrt(np.mean((np.clip(got, 0, 1) - np.clip(want, 0, 1)) ** 2)))
     assert rmse < tol, rmse
+
+
+def test_coplanar_rays_are_the_known_hit_or_miss_class():
+    """DESIGN.md section 1, second degenerate class: two shadow rays of the bench's incoherent batch that lie in the plane of
+    the emitter triangle they 'hit'.  det = n.d is rounding noise, the computed hit point lies outside the triangle's bounds;
+    the exact boxes of the reference layout cull the leaf (oracle: miss), the quantised 8-wide boxes do not (walker and CUDA
+    path on the converted tree: hit)."""
+    from imbatracer_b200 import procedural
+    flat = procedural.still_life_proxy(1.0)
+    rays = np.zeros(2, abi.RAY)
+    rays[0] = ((1.8839427, 7.1488204, 4.8558984), 0.001, (-0.02364074, -0.045666218, 0.2283302), 0.999)
+    rays[1] = ((3.3762798, 6.1687307, -0.2962015), 0.001, (-0.09021112, -0.20622504, -0.05316282), 0.999)
+    assert (refapi.trace_oracle(flat, rays)["tri_id"] == -1).all() and (refapi.trace_oracle(flat, rays, any_hit=True)["tri_id"] == -1).all()
+    w = refapi.Bvh8Host(flat).walk(rays)
+    assert w["tri_id"].tolist() == [1516449, 1516456]
+    idx = flat.indices.reshape(-1, 4); v = flat.vertices.reshape(-1, 4)[:, :3].astype(np.float64)
+    for r, h in zip(rays, w):
+        p0, p1, p2 = v[idx[h["tri_id"], :3]]
+        n = np.cross(p0 - p1, p2 - p0); d = r["dir"].astype(np.float64)
+        assert abs(n @ d) < 1e-6 * np.linalg.norm(n) * np.linalg.norm(d)          # the ray lies in the triangle's plane
+        p = r["org"].astype(np.float64) + float(h["tmax"]) * d
+        lo, hi = np.minimum(np.minimum(p0, p1), p2), np.maximum(np.maximum(p0, p1), p2)
+        assert ((p < lo - 1e-3) | (p > hi + 1e-3)).any()                          # the reported point is not on the triangle

@@ -7,7 +7,7 @@ from imbatracer_b200 import api, abi
 import hashlib
 if os.environ.get('IMBA_LIB_VARIANT'):
     abi.LIB_PATH = os.path.join(os.path.dirname(abi.LIB_PATH), os.environ['IMBA_LIB_VARIANT'])
-flat = bench.load_flat(); scene = api.Scene(flat); n = bench.RAYS_PER_BATCH
+flat = bench.load_flat(); scene = api.Scene(flat, device_build=bool(os.environ.get("IMBA_DEVICE_BUILD"))); n = bench.RAYS_PER_BATCH
 cache = "/tmp/bench_batches.npz"
 if os.path.exists(cache):
     z = np.load(cache); batches = {k: z[k].view(api.abi.RAY).reshape(-1) for k in z.files}
