@@ -251,13 +251,14 @@ def run_pt(scene, flat, rank, world, barrier, dist, iters, width=1920, height=10
     integ = api.Integrator(scene, api.render_settings(flat, "pt", width, height, spp=1, max_path_len=10, seed=0x1234ABCD, rank=rank, rank_count=world))
     from imbatracer_b200.distributed import ProgressiveRenderer
     integ.preprocess()
-    loop = ProgressiveRenderer(integ, width, height)   # integ.render(1) + NCCL sum of the framebuffer, per iteration
+    loop = ProgressiveRenderer(integ, width, height)   # integ.render(1) + NCCL sum of the framebuffer per iteration (overlapped with the next one)
     stream = loop.stream
     loop.step(2)
-    integ.sync(); barrier()
+    loop.finish(); integ.sync(); barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     loop.step(iters)
+    loop.finish()                      # the framebuffer sums run on a second stream; the timed region ends after the last one
     e1.record(stream)
     integ.sync(); barrier()
     ms = e0.elapsed_time(e1)

@@ -86,6 +86,18 @@ extern "C" imba_integrator* imba_integrator_create(imba_scene* scene, const imba
 
 extern "C" int imba_integrator_set_framebuffer(imba_integrator* it, float* d_rgb) {
     if (!it || !d_rgb) { imba_set_error("null argument"); return IMBA_ERR_INVALID; }
+    if (d_rgb == it->fb) return IMBA_OK;
+    // the tail graph of the VCM light pass captured launches that write to the current framebuffer: park it under that
+    // pointer and pick up the one captured for the new framebuffer, if any (callers alternate between two buffers to overlap
+    // the multi-GPU sum with the next iteration)
+    if (it->tail_graph) {
+        int slot = -1;
+        for (int i = 0; i < imba_integrator::kParkedGraphs && slot < 0; ++i) if (!it->parked_graph[i]) slot = i;
+        if (slot < 0) { cudaGraphExecDestroy(it->parked_graph[0]); slot = 0; }
+        it->parked_fb[slot] = it->fb; it->parked_graph[slot] = it->tail_graph; it->tail_graph = nullptr;
+    }
+    for (int i = 0; i < imba_integrator::kParkedGraphs; ++i)
+        if (it->parked_graph[i] && it->parked_fb[i] == d_rgb) { it->tail_graph = it->parked_graph[i]; it->parked_graph[i] = nullptr; it->parked_fb[i] = nullptr; }
     if (it->owns_fb) cudaFree(it->fb);
     it->fb = d_rgb; it->owns_fb = false;
     return IMBA_OK;

@@ -75,6 +75,9 @@ struct imba_integrator {
     struct VcmParams* d_params = nullptr;    // per-iteration constants in device memory
     unsigned* tail_counters = nullptr; int tail_counter_next = -1; // dedicated traversal work counters of the captured graph
     cudaGraphExec_t tail_graph = nullptr;    // captured light-pass wavefronts for the long tail of small queues
+    // the captured launches hold the framebuffer pointer: graphs of other framebuffers the caller alternates between are parked here
+    static constexpr int kParkedGraphs = 4;
+    float* parked_fb[kParkedGraphs] = {}; cudaGraphExec_t parked_graph[kParkedGraphs] = {};
 };
 int imba_vcm_allocate(imba_integrator* it);
 void imba_vcm_free(imba_integrator* it);

@@ -135,6 +135,7 @@ static int light_pass(imba_integrator* it, int algo, uint32_t seed_base, int pat
 
 void imba_vcm_free(imba_integrator* it) {
     if (it->tail_graph) { cudaGraphExecDestroy(it->tail_graph); it->tail_graph = nullptr; }
+    for (int i = 0; i < imba_integrator::kParkedGraphs; ++i) if (it->parked_graph[i]) { cudaGraphExecDestroy(it->parked_graph[i]); it->parked_graph[i] = nullptr; }
     cudaFree(it->d_params); it->d_params = nullptr; cudaFree(it->tail_counters); it->tail_counters = nullptr;
     cudaFree(it->cache); cudaFree(it->cache_last); cudaFree(it->grid); cudaFree(it->grid_bbox); cudaFree(it->cells); cudaFree(it->block_sums); cudaFree(it->photons);
     it->cache = nullptr; it->cache_last = nullptr; it->grid = nullptr; it->grid_bbox = nullptr; it->cells = nullptr; it->block_sums = nullptr; it->photons = nullptr;

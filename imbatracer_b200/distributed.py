@@ -32,24 +32,53 @@ class _null:
 
 class ProgressiveRenderer:
     """Render loop of frontend/render_window.cpp:50-95 for N ranks: integrator.render(1) + framebuffer sum per iteration.
-    `image()` = total / (iterations * world * spp), the normalisation of render_window.cpp:105,178."""
+    `image()` = total / (iterations * world * spp), the normalisation of render_window.cpp:105,178.
 
-    def __init__(self, integrator, width, height, spp=1, group=None):
+    With more than one rank the sum is taken off the critical path: the integrator renders alternately into two framebuffers,
+    and the NCCL sum + accumulation of iteration k runs on a second stream while iteration k+1 is being rendered (events order
+    the hand-over both ways), so the collective costs no device time as long as it is shorter than one iteration."""
+
+    def __init__(self, integrator, width, height, spp=1, group=None, overlap=None):
         self.integ, self.group, self.spp = integrator, group, spp
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
-        self.fb = torch.zeros(width * height * 3, dtype=torch.float32, device="cuda")
+        self.overlap = (self.world > 1) if overlap is None else bool(overlap)
+        self.fbs = [torch.zeros(width * height * 3, dtype=torch.float32, device="cuda") for _ in range(2 if self.overlap else 1)]
+        self.fb = self.fbs[0]
         self.total = torch.zeros_like(self.fb)
         self.integ.set_framebuffer(self.fb)
         self.stream = torch.cuda.ExternalStream(self.integ.stream_ptr())
+        if self.overlap:
+            self.comm = torch.cuda.Stream()
+            self.rendered = [torch.cuda.Event() for _ in range(2)]
+            self.consumed = [torch.cuda.Event() for _ in range(2)]
+            for e in self.consumed:
+                e.record(self.comm)
         self.iterations = 0
         self.shape = (height, width, 3)
 
     def step(self, iterations=1):
         for _ in range(iterations):
-            self.integ.render(1)
-            accumulate_iteration(self.fb, self.total, self.group, self.stream)
+            if not self.overlap:
+                self.integ.render(1)
+                accumulate_iteration(self.fb, self.total, self.group, self.stream)
+            else:
+                k = self.iterations % 2
+                self.stream.wait_event(self.consumed[k])          # buffer k was summed and cleared two iterations ago
+                self.integ.set_framebuffer(self.fbs[k])
+                self.integ.render(1)
+                self.rendered[k].record(self.stream)
+                self.comm.wait_event(self.rendered[k])
+                accumulate_iteration(self.fbs[k], self.total, self.group, self.comm)
+                self.consumed[k].record(self.comm)
             self.iterations += 1
 
+    def finish(self):
+        """Orders everything outstanding on the reduction stream before later work on the integrator's stream."""
+        if self.overlap:
+            for e in self.consumed:
+                self.stream.wait_event(e)
+
     def image(self):
+        self.finish()
         self.integ.sync()
         return (self.total / float(self.iterations * self.world * self.spp)).reshape(self.shape)
