@@ -276,6 +276,25 @@ def run_pt(scene, flat, rank, world, barrier, dist, iters, width=1920, height=10
             "framebuffer_allreduce_bytes": width * height * 12 if dist is not None else 0, "mean_radiance": mean}
 
 
+def run_integrators(scene, flat, width=1920, height=1080, iters=4):
+    """configs[3]: the bidirectional family at 1080p on the bench scene (rank 0, untimed region): light paths = W*H/2
+    (test/run_bench.py:111), 1 connection, k = 10; ms per progressive iteration and rays per second."""
+    from imbatracer_b200 import api
+    out = {}
+    for algo in ("bpt", "vcm", "lt", "ppm"):
+        it = api.Integrator(scene, api.render_settings(flat, algo, width, height, seed=5))
+        it.preprocess(); it.render(1); it.sync()
+        p0, s0 = it.ray_counts()
+        t0 = time.perf_counter(); it.render(iters); it.sync(); dt = time.perf_counter() - t0
+        p1, s1 = it.ray_counts()
+        img = it.download()
+        it.close()
+        out[algo] = {"ms_per_iteration": dt / iters * 1e3, "samples_per_s": width * height * iters / dt, "mrays_s": (p1 - p0 + s1 - s0) / dt / 1e6,
+                     "mean_radiance": float(img.mean()) / (iters + 1)}
+    out["workload"] = f"{width}x{height}, light paths W*H/2, 1 connection, 10 nearest photons, max path length 10, {SCENE}"
+    return out
+
+
 def device_build_entry(flat, d_rays, hits, n):
     """Row f1 end to end: imba_scene_create with IMBA_ACCEL_DEVICE_BUILD (LBVH + 8-wide collapse + emission on the device,
     csrc/bvh8_gpu.cu) and closest-hit traversal of the same rays on the resulting tree."""
@@ -458,7 +477,7 @@ def run_ours(args):
                         "steps": e2e_steps, "note": "imba_trace_host on pinned host queues, wall clock with device sync"},
                 "gpu_launches": int(launches),
                 "clocks": sampler.summary(),
-                "pt": pt, "cfg0": ours_cfg0(), "scenes": run_extra_scenes(rank), "device_build": device_build,
+                "pt": pt, "cfg0": ours_cfg0(), "integrators": run_integrators(scene, flat), "scenes": run_extra_scenes(rank), "device_build": device_build,
                 "per_kernel": {name: {"ms": per_kernel_ms[i], "mrays_s": n / per_kernel_ms[i] / 1e3} for i, (name, _) in enumerate(BATCH_ORDER)},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(),
                              "kernel": "trace_kernel<closest> on the incoherent batch", "peak_source": peak_src,

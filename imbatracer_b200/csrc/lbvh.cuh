@@ -190,15 +190,22 @@ __global__ void ploc_nearest_kernel(const int* cid, int count, const Box6* boxes
     if (i >= count) return;
     const Box6 me = tile[threadIdx.x + PLOC_RADIUS];
     float best = FLT_MAX; int bj = -1;
-    for (int o = -PLOC_RADIUS; o <= PLOC_RADIUS; ++o) {
-        const int j = i + o;
-        if (o == 0 || j < 0 || j >= count) continue;
-        const Box6& ot = tile[threadIdx.x + PLOC_RADIUS + o];
-        const float dx = fmaxf(me.v[3], ot.v[3]) - fminf(me.v[0], ot.v[0]), dy = fmaxf(me.v[4], ot.v[4]) - fminf(me.v[1], ot.v[1]),
-                    dz = fmaxf(me.v[5], ot.v[5]) - fminf(me.v[2], ot.v[2]);
-        const float d = dx * dy + dy * dz + dz * dx;
-        if (d < best) { best = d; bj = j; }   // ties: the lower index wins (o ascends), which guarantees a mutual pair exists
+    // candidates by increasing index distance; at equal distance even positions look right first, odd ones left first; a
+    // candidate wins only when strictly better.  On ties (duplicated geometry: all distances equal) this pairs (0,1), (2,3), ...
+    // instead of one pair per round, and a mutual pair always exists.
+    for (int k = 1; k <= PLOC_RADIUS; ++k) {
+        for (int side = 0; side < 2; ++side) {
+            const int o = ((i & 1) == side) ? k : -k;
+            const int j = i + o;
+            if (j < 0 || j >= count) continue;
+            const Box6& ot = tile[threadIdx.x + PLOC_RADIUS + o];
+            const float dx = fmaxf(me.v[3], ot.v[3]) - fminf(me.v[0], ot.v[0]), dy = fmaxf(me.v[4], ot.v[4]) - fminf(me.v[1], ot.v[1]),
+                        dz = fmaxf(me.v[5], ot.v[5]) - fminf(me.v[2], ot.v[2]);
+            const float d = dx * dy + dy * dz + dz * dx;
+            if (d < best) { best = d; bj = j; }
+        }
     }
+    if (bj < 0) bj = i > 0 ? i - 1 : 1;   // NaN boxes: still pair up
     nearest[i] = bj;
 }
 
@@ -242,8 +249,9 @@ inline cudaError_t ploc_build_tree(const MeshView& m, LbvhTree& t) {
     lbvh_morton_kernel<<<blocks, 256>>>(m, t.bbox.as<int>(), t.keys.as<unsigned long long>(), t.ids.as<int>());
     LBT(cub::DeviceRadixSort::SortPairs(t.temp.p, temp_bytes, t.keys.as<unsigned long long>(), t.keys2.as<unsigned long long>(), t.ids.as<int>(), t.ids2.as<int>(), n, 0, 63));
     ploc_leaf_kernel<<<blocks, 256>>>(m, t.ids2.as<int>(), n, t.boxes.as<Box6>(), cidA.as<int>());
-    int launches = 4, count = n;
+    int launches = 4, count = n, rounds = 0;
     while (count > 1) {
+        if (++rounds > 4096) return cudaErrorUnknown;
         const int b = (count + 255) / 256;
         ploc_nearest_kernel<<<b, 256>>>(cidA.as<int>(), count, t.boxes.as<Box6>(), nearest.as<int>());
         ploc_merge_kernel<<<b, 256>>>(cidA.as<int>(), count, nearest.as<int>(), t.boxes.as<Box6>(), t.children.as<int2>(), t.parent.as<int>(), counters.as<int>(), cidB.as<int>());

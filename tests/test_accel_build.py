@@ -125,9 +125,21 @@ def _tiny_two_mesh_scene():
     return procedural.build_accel(t)
 
 
+def _duplicated_geometry_scene(copies=300):
+    """Every triangle of a tiny terrain `copies` times: all centroids and boxes coincide in groups (worst case for the
+    clustering builder's tie handling and for the Morton split)."""
+    t = procedural.terrain(3)
+    a = t.arrays
+    nt = t.tri_count
+    a["indices"] = np.tile(a["indices"].reshape(-1, 4), (copies, 1)).reshape(-1).copy()
+    a["geom_normals"] = np.tile(a["geom_normals"].reshape(-1, 4), (copies, 1)).reshape(-1).copy()
+    a["mesh_tri_base"] = np.array([0, nt * copies], np.int32)
+    return procedural.build_accel(t)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("builder", ["ploc", "lbvh"])
-@pytest.mark.parametrize("name", ["instanced", "terrain", "proxy", "one_triangle"])
+@pytest.mark.parametrize("name", ["instanced", "terrain", "proxy", "one_triangle", "duplicates"])
 def test_device_built_structure_gives_identical_traversal_results(scenes, name, builder, monkeypatch):
     """csrc/bvh8_gpu.cu (IMBA_ACCEL_DEVICE_BUILD): linear BVH + SAH-optimal 8-wide collapse + emission, all on the device,
     straight from the meshes.  A different tree again; hits must equal the oracle's on the host-built reference-layout tree."""
@@ -136,6 +148,8 @@ def test_device_built_structure_gives_identical_traversal_results(scenes, name, 
     monkeypatch.setenv("IMBA_GPU_BUILDER", builder)     # binary tree: parallel locally-ordered clustering (default) or Karras LBVH
     if name == "proxy":
         s = procedural.still_life_proxy(0.02)
+    elif name == "duplicates":
+        s = _duplicated_geometry_scene()
     elif name == "one_triangle":   # degenerate mesh sizes: a single-triangle mesh instanced twice next to a two-triangle mesh
         s = _tiny_two_mesh_scene()
     else:
