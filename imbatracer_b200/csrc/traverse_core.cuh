@@ -187,4 +187,120 @@ __device__ __noinline__ bool trace_single(const TraceArgs& P, const float4 o, co
     }
 }
 
+/* ---- one ray traced by a whole warp ------------------------------------------------------------------------------------------
+ * For the few very long light paths at the end of a light pass (vcm.cu: vcm_light_tail_warp_kernel) latency matters, not
+ * throughput: the 8 child boxes of a node are tested by 8 lanes and the triangles of a leaf group by one lane each, so one
+ * traversal step costs ~1/6 of the dependent instructions of the one-thread version.  All lanes hold the same ray, stack and
+ * hit; every box / triangle test is the very same arithmetic as in node_step / tri_test, child results are OR-ed and triangle
+ * candidates reduced with the (t, tri, inst) order, so the result is bit-identical to trace_single and trace_kernel. */
+__device__ __forceinline__ uint32_t node_step_coop(const uint4 n0, const uint4 n1, const uint4 n2, const uint4 n3, const uint4 n4, const RayRegs& r, float tmin, float tbest, unsigned lane) {
+    const uint32_t e_imask = n0.w;
+    const float adjx = __uint_as_float((e_imask & 0xffu) << 23) * r.ix;
+    const float adjy = __uint_as_float(((e_imask >> 8) & 0xffu) << 23) * r.iy;
+    const float adjz = __uint_as_float(((e_imask >> 16) & 0xffu) << 23) * r.iz;
+    const float orgx = (__uint_as_float(n0.x) - r.ox) * r.ix;
+    const float orgy = (__uint_as_float(n0.y) - r.oy) * r.iy;
+    const float orgz = (__uint_as_float(n0.z) - r.oz) * r.iz;
+    uint32_t contrib = 0;
+    if (lane < 8u) {
+        const bool half = lane >= 4u; const int j = (int)(lane & 3u);
+        const uint32_t meta4 = half ? n1.w : n1.z;
+        const uint32_t is_inner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
+        const uint32_t inner_mask4 = sign_extend_s8x4(is_inner4 << 3);
+        const uint32_t bit_index4 = (meta4 ^ (r.octinv4 & inner_mask4)) & 0x1f1f1f1fu;
+        const uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
+        const uint32_t qlox = half ? n2.y : n2.x, qloy = half ? n2.w : n2.z, qloz = half ? n3.y : n3.x;
+        const uint32_t qhix = half ? n3.w : n3.z, qhiy = half ? n4.y : n4.x, qhiz = half ? n4.w : n4.z;
+        const uint32_t nx = r.ix < 0.0f ? qhix : qlox, fx = r.ix < 0.0f ? qlox : qhix;
+        const uint32_t ny = r.iy < 0.0f ? qhiy : qloy, fy = r.iy < 0.0f ? qloy : qhiy;
+        const uint32_t nz = r.iz < 0.0f ? qhiz : qloz, fz = r.iz < 0.0f ? qloz : qhiz;
+        const float t0x = __fmaf_rn(byte_f(nx, j), adjx, orgx), t1x = __fmaf_rn(byte_f(fx, j), adjx, orgx);
+        const float t0y = __fmaf_rn(byte_f(ny, j), adjy, orgy), t1y = __fmaf_rn(byte_f(fy, j), adjy, orgy);
+        const float t0z = __fmaf_rn(byte_f(nz, j), adjz, orgz), t1z = __fmaf_rn(byte_f(fz, j), adjz, orgz);
+        const float tn = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, tmin));
+        const float tf = fminf(fminf(t1x, t1y), fminf(t1z, tbest));
+        if (tn <= tf * IMBA_ROBUST_TFAR) {
+            const uint32_t cb = (child_bits4 >> (8 * j)) & 0xffu, bi = (bit_index4 >> (8 * j)) & 0xffu;
+            contrib = cb << bi;
+        }
+    }
+    return __reduce_or_sync(0xffffffffu, contrib);
+}
+
+/* Must be called by all 32 lanes with identical arguments; returns the same result in every lane. */
+template <bool ANY, bool MASKS>
+__device__ __noinline__ bool trace_warp(const TraceArgs& P, const float4 o, const float4 d, HitRegs& h) {
+    const unsigned lane = threadIdx.x & 31u;
+    uint2 stack[IMBA_TRAVERSAL_STACK];
+    int sp = 0;
+    RayRegs r; r.ox = o.x; r.oy = o.y; r.oz = o.z; r.dx = d.x; r.dy = d.y; r.dz = d.z;
+    if (P.flat_inst >= 0) { r.ox += 0.0f; r.oy += 0.0f; r.oz += 0.0f; r.dx += 0.0f; r.dy += 0.0f; r.dz += 0.0f; }
+    r.finish();
+    const float tmin = o.w;
+    h.tbest = d.w; h.ubest = 0.0f; h.tri_best = IMBA_NO_HIT; h.inst_best = IMBA_NO_HIT;
+    int cur_inst = P.flat_inst;
+    uint2 ngroup = make_uint2(P.top_root, 0x80000000u), tgroup = make_uint2(0, 0);
+    for (;;) {
+        if (ngroup.y > 0x00ffffffu) {
+            const uint32_t hits = ngroup.y;
+            const uint32_t bit = 31u - (uint32_t)__clz(hits);
+            ngroup.y &= ~(1u << bit);
+            if (ngroup.y > 0x00ffffffu) stack[sp++] = ngroup;
+            const uint32_t slot = (bit - 24u) ^ (r.octinv4 & 0xffu);
+            const uint32_t rel = __popc(hits & 0xffu & ~(0xffffffffu << slot));
+            const uint4* np = P.nodes + (size_t)(ngroup.x + rel) * 5;
+            const uint4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
+            const uint32_t hitmask = node_step_coop(n0, n1, n2, n3, n4, r, tmin, h.tbest, lane);
+            ngroup = make_uint2(n1.x, (hitmask & 0xff000000u) | (n0.w >> 24));
+            tgroup = make_uint2(n1.y, hitmask & 0x00ffffffu);
+        } else { tgroup = ngroup; ngroup = make_uint2(0, 0); }
+        if (tgroup.y != 0) {
+            if (cur_inst < 0) { // top level: instances one at a time, as in trace_single
+                const uint32_t bit = 31u - (uint32_t)__clz(tgroup.y);
+                tgroup.y &= ~(1u << bit);
+                if (ngroup.y > 0x00ffffffu) stack[sp++] = ngroup;
+                if (tgroup.y != 0) stack[sp++] = tgroup;
+                stack[sp++] = make_uint2(0xffffffffu, 0u);
+                const float4* ip = P.insts + (size_t)(tgroup.x + bit) * 4;
+                const float4 m0 = __ldg(ip), m1 = __ldg(ip + 1), m2 = __ldg(ip + 2);
+                const int4 id = __ldg((const int4*)(ip + 3));
+                enter_instance(r, m0, m1, m2);
+                cur_inst = id.x;
+                ngroup = make_uint2((uint32_t)id.y, 0x80000000u);
+                tgroup = make_uint2(0, 0);
+            } else {            // one triangle of the group per lane
+                const unsigned pos = __fns(tgroup.y, 0u, (int)lane + 1);
+                HitRegs mine = h; bool got = false;
+                if (pos != 0xffffffffu) {
+                    const float4* tp = P.tris + (size_t)(tgroup.x + pos) * 3;
+                    got = tri_test<MASKS>(P, __ldg(tp), __ldg(tp + 1), __ldg(tp + 2), r, tmin, cur_inst, mine);
+                }
+                tgroup.y = 0;
+                if (ANY) {
+                    if (__any_sync(0xffffffffu, got)) { h = mine; return true; }
+                } else {
+#pragma unroll
+                    for (int off = 16; off > 0; off >>= 1) {
+                        const float ot = __shfl_xor_sync(0xffffffffu, mine.tbest, off), ou = __shfl_xor_sync(0xffffffffu, mine.ubest, off);
+                        const int otri = __shfl_xor_sync(0xffffffffu, mine.tri_best, off), oinst = __shfl_xor_sync(0xffffffffu, mine.inst_best, off);
+                        if (ot < mine.tbest || (ot == mine.tbest && (otri < mine.tri_best || (otri == mine.tri_best && oinst < mine.inst_best)))) {
+                            mine.tbest = ot; mine.ubest = ou; mine.tri_best = otri; mine.inst_best = oinst;
+                        }
+                    }
+                    h = mine;
+                }
+            }
+        }
+        if (ngroup.y <= 0x00ffffffu && tgroup.y == 0) {
+            for (;;) {
+                if (sp == 0) return h.tri_best != IMBA_NO_HIT;
+                const uint2 e = stack[--sp];
+                if (e.y == 0u) { r.ox = o.x; r.oy = o.y; r.oz = o.z; r.dx = d.x; r.dy = d.y; r.dz = d.z; r.finish(); cur_inst = -1; continue; }
+                ngroup = e;
+                break;
+            }
+        }
+    }
+}
+
 #endif

@@ -189,20 +189,22 @@ __global__ void __launch_bounds__(128) vcm_light_shade_kernel(const DeviceShadin
 template <int ALGO, bool MASKS>
 __global__ void __launch_bounds__(64) vcm_light_tail_kernel(const DeviceShading S, const VcmParams* Pd, const DevCamera cam, const TraceArgs T, const float4* rays,
                                                             const VCMState* states, const int* count_ptr, DevLightVertex* cache, int cache_capacity, int* cache_last,
-                                                            float* fb, unsigned long long* ray_stats, int max_bounces) {
+                                                            float* fb, unsigned long long* ray_stats, int max_bounces,
+                                                            float4* out_rays, VCMState* out_states, int* out_count) {
     const VcmParams P = *Pd;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= *count_ptr) return;
     float4 ro = rays[2 * i], rd = rays[2 * i + 1];
     VCMState st = states[i];
     unsigned long long traced = 0, shadows = 0;
+    bool alive = true;
     for (int bounce = 0; bounce < max_bounces; ++bounce) {
         HitRegs hr;
         ++traced;
-        if (!trace_single<false, MASKS>(T, ro, rd, hr)) break;
+        if (!trace_single<false, MASKS>(T, ro, rd, hr)) { alive = false; break; }
         const int4 h = make_int4(hr.tri_best, hr.inst_best, __float_as_int(hr.tbest), __float_as_int(hr.ubest));
         bool has_shadow; float4 sh_o, sh_d; ShadowState ss;
-        const bool alive = light_vertex<ALGO>(S, P, cam, ro, rd, h, st, cache, cache_capacity, cache_last, has_shadow, sh_o, sh_d, ss);
+        alive = light_vertex<ALGO>(S, P, cam, ro, rd, h, st, cache, cache_capacity, cache_last, has_shadow, sh_o, sh_d, ss);
         if (has_shadow) {
             ++shadows;
             HitRegs occ;
@@ -210,7 +212,54 @@ __global__ void __launch_bounds__(64) vcm_light_tail_kernel(const DeviceShading 
         }
         if (!alive) break;
     }
+    if (alive && out_count) { // bounce budget used up: hand the path to the warp-per-path kernel
+        const int slot = atomicAdd(out_count, 1);
+        out_rays[2 * slot] = ro; out_rays[2 * slot + 1] = rd; out_states[slot] = st;
+    }
     if (ray_stats) { atomicAdd(ray_stats, traced); atomicAdd(ray_stats + 1, shadows); }
+}
+
+/* The longest light paths (thousands of bounces inside glass): one WARP per path, traversal by trace_warp (traverse_core.cuh),
+ * vertex processing by lane 0.  Same functions, same RNG stream, same results as the kernels above; only the latency of one
+ * bounce differs. */
+template <int ALGO, bool MASKS>
+__global__ void __launch_bounds__(128) vcm_light_tail_warp_kernel(const DeviceShading S, const VcmParams* Pd, const DevCamera cam, const TraceArgs T, const float4* rays,
+                                                                  const VCMState* states, const int* count_ptr, DevLightVertex* cache, int cache_capacity, int* cache_last,
+                                                                  float* fb, unsigned long long* ray_stats, int max_bounces) {
+    const VcmParams P = *Pd;
+    const unsigned lane = threadIdx.x & 31u;
+    const int warps = (gridDim.x * blockDim.x) >> 5, count = *count_ptr;
+    unsigned long long traced = 0, shadows = 0;
+    for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < count; i += warps) {
+        float4 ro = rays[2 * i], rd = rays[2 * i + 1];
+        VCMState st = states[i];
+        for (int bounce = 0; bounce < max_bounces; ++bounce) {
+            HitRegs hr;
+            ++traced;
+            if (!trace_warp<false, MASKS>(T, ro, rd, hr)) break;
+            const int4 h = make_int4(hr.tri_best, hr.inst_best, __float_as_int(hr.tbest), __float_as_int(hr.ubest));
+            int flags = 0; float4 sh_o = make_float4(0, 0, 0, 0), sh_d = sh_o; ShadowState ss;
+            if (lane == 0) {
+                bool has_shadow;
+                const bool alive = light_vertex<ALGO>(S, P, cam, ro, rd, h, st, cache, cache_capacity, cache_last, has_shadow, sh_o, sh_d, ss);
+                flags = (alive ? 1 : 0) | (has_shadow ? 2 : 0);
+            }
+            __syncwarp();
+            flags = __shfl_sync(0xffffffffu, flags, 0);
+            ro.x = __shfl_sync(0xffffffffu, ro.x, 0); ro.y = __shfl_sync(0xffffffffu, ro.y, 0); ro.z = __shfl_sync(0xffffffffu, ro.z, 0); ro.w = __shfl_sync(0xffffffffu, ro.w, 0);
+            rd.x = __shfl_sync(0xffffffffu, rd.x, 0); rd.y = __shfl_sync(0xffffffffu, rd.y, 0); rd.z = __shfl_sync(0xffffffffu, rd.z, 0); rd.w = __shfl_sync(0xffffffffu, rd.w, 0);
+            if (flags & 2) {
+                sh_o.x = __shfl_sync(0xffffffffu, sh_o.x, 0); sh_o.y = __shfl_sync(0xffffffffu, sh_o.y, 0); sh_o.z = __shfl_sync(0xffffffffu, sh_o.z, 0); sh_o.w = __shfl_sync(0xffffffffu, sh_o.w, 0);
+                sh_d.x = __shfl_sync(0xffffffffu, sh_d.x, 0); sh_d.y = __shfl_sync(0xffffffffu, sh_d.y, 0); sh_d.z = __shfl_sync(0xffffffffu, sh_d.z, 0); sh_d.w = __shfl_sync(0xffffffffu, sh_d.w, 0);
+                ++shadows;
+                HitRegs occ;
+                const bool blocked = trace_warp<true, MASKS>(T, sh_o, sh_d, occ);
+                if (!blocked && lane == 0) add_contribution(fb, ss.pixel_id, v3(ss.r, ss.g, ss.b));
+            }
+            if (!(flags & 1)) break;
+        }
+    }
+    if (ray_stats && lane == 0) { atomicAdd(ray_stats, traced); atomicAdd(ray_stats + 1, shadows); }
 }
 
 /* ---- photon hash grid (rangesearch.h) ------------------------------------------------------------------------- */
@@ -569,8 +618,17 @@ cudaError_t imba_vcm_camera_shade(int algo, const VcmLaunch& a, cudaStream_t st)
 
 cudaError_t imba_vcm_light_tail(int algo, bool masks, const VcmLaunch& a, const TraceArgs& T, int capacity, cudaStream_t st) {
     if (capacity <= 0) return cudaSuccess;
-    const int grid = (capacity + 63) / 64, max_bounces = 1 << 20;
-#define TAIL(A, M) vcm_light_tail_kernel<A, M><<<grid, 64, 0, st>>>(*a.S, a.P, a.cam, T, a.rays, a.states, a.queue_count_ptr, a.cache, a.cache_capacity, a.cache_last, a.fb, a.ray_stats, max_bounces)
+    // stage 1: one thread per path for up to `budget` bounces (most paths end here); stage 2: the survivors, one warp per path
+    const int budget = getenv("IMBA_TAIL_BUDGET") ? atoi(getenv("IMBA_TAIL_BUDGET")) : 24;
+    const bool two_stage = budget > 0 && a.out_rays && a.out_states && a.out_count;
+    const int grid = (capacity + 63) / 64, unlimited = 1 << 20;
+    if (two_stage) { const cudaError_t e = cudaMemsetAsync(a.out_count, 0, sizeof(int), st); if (e != cudaSuccess) return e; }
+    const int grid2 = std::min((capacity + 3) / 4, 148 * 8);
+#define TAIL(A, M) do { \
+        vcm_light_tail_kernel<A, M><<<grid, 64, 0, st>>>(*a.S, a.P, a.cam, T, a.rays, a.states, a.queue_count_ptr, a.cache, a.cache_capacity, a.cache_last, a.fb, a.ray_stats, \
+                                                         two_stage ? budget : unlimited, two_stage ? a.out_rays : nullptr, two_stage ? a.out_states : nullptr, two_stage ? a.out_count : nullptr); \
+        if (two_stage) vcm_light_tail_warp_kernel<A, M><<<grid2, 128, 0, st>>>(*a.S, a.P, a.cam, T, a.out_rays, a.out_states, a.out_count, a.cache, a.cache_capacity, a.cache_last, \
+                                                                             a.fb, a.ray_stats, unlimited); } while (0)
     switch (algo) {
         case IMBA_ALGO_BPT: if (masks) TAIL(IMBA_ALGO_BPT, true); else TAIL(IMBA_ALGO_BPT, false); break;
         case IMBA_ALGO_PPM: if (masks) TAIL(IMBA_ALGO_PPM, true); else TAIL(IMBA_ALGO_PPM, false); break;

@@ -107,7 +107,7 @@ static int light_pass(imba_integrator* it, int algo, uint32_t seed_base, int pat
             TraceArgs T; imba_scene_trace_args(it->scene, &T);
             const VcmLaunch a = base_launch(it, cur, n);
             IMBA_CUDA(imba_vcm_light_tail(algo, it->scene->has_masks, a, T, n, it->stream), IMBA_ERR_CUDA);
-            g_imba_launches.fetch_add(1); ++w;
+            g_imba_launches.fetch_add(2); ++w;
             break;
         }
         const int tail_rays = std::min(TAIL_RAYS, it->capacity);

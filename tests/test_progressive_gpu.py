@@ -31,3 +31,32 @@ def test_overlapped_accumulation_equals_plain_loop(algo):
     # same seeds, same iterations: only the order of the atomic float adds inside an iteration differs
     assert abs(a.sum() - b.sum()) <= 2e-4 * a.sum()
     assert np.abs(a - b).max() <= 1e-3 * max(1.0, a.max())
+
+
+@pytest.mark.parametrize("algo", ["lt", "ppm", "vcm"])
+def test_warp_per_path_tail_equals_thread_per_path_tail(algo, monkeypatch):
+    """csrc/vcm.cu: after a bounce budget the light-path tail hands the survivors to a kernel that traces ONE path per WARP
+    (traverse_core.cuh: trace_warp: 8 lanes test the 8 children of a node, one lane per triangle of a leaf).  Same arithmetic,
+    so the ray counts must be identical and the images equal up to the order of the atomic float adds (LT, PPM).  VCM connects
+    camera vertices to cache entries picked BY INDEX, and the order of the atomic appends to the cache is not reproducible from
+    run to run in any variant: there only the light-pass ray count is exact, the rest statistical."""
+    from imbatracer_b200 import api
+    flat = load_scene("cornell_water", "gpu")     # glass surface and spheres: light paths with hundreds of bounces
+    sc = api.Scene(flat)
+    out = []
+    for budget in ("0", "3", "24"):               # 0 = the one-stage thread-per-path tail; 3 = nearly everything goes through the warp kernel
+        monkeypatch.setenv("IMBA_TAIL_BUDGET", budget)
+        it = api.Integrator(sc, api.render_settings(flat, algo, 160, 120, seed=21))
+        it.preprocess(); it.render(3)
+        img = it.download(); counts = it.ray_counts()
+        it.close()
+        out.append((img, counts))
+    sc.close()
+    for img, counts in out[1:]:
+        if algo == "vcm":
+            assert counts[0] == out[0][1][0] and abs(counts[1] - out[0][1][1]) <= 2e-3 * counts[1], (counts, out[0][1])
+            assert abs(img.sum() - out[0][0].sum()) <= 0.03 * out[0][0].sum()
+            continue
+        assert counts == out[0][1], (counts, out[0][1])
+        assert abs(img.sum() - out[0][0].sum()) <= 2e-4 * out[0][0].sum()
+        assert np.abs(img - out[0][0]).max() <= 1e-3 * max(1.0, out[0][0].max())
