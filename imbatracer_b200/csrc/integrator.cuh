@@ -71,6 +71,7 @@ struct imba_integrator {
     struct DevLightVertex* cache = nullptr; int cache_capacity = 0; int* cache_last = nullptr;
     struct GridParams* grid = nullptr; int* grid_bbox = nullptr; int* cells = nullptr; unsigned table = 0; int* block_sums = nullptr;
     struct DevPhoton* photons = nullptr;
+    float4* photon_pos = nullptr; int* merge_found = nullptr; // SoA copy of the photon positions; k-NN lists of the camera wavefront
     float   base_radius = 0.0f;
     struct VcmParams* d_params = nullptr;    // per-iteration constants in device memory
     unsigned* tail_counters = nullptr; int tail_counter_next = -1; // dedicated traversal work counters of the captured graph

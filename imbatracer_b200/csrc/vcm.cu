@@ -359,7 +359,7 @@ __global__ void scan_add_kernel(int* data, int n, const int* block_sums) {
     if (i < n) data[i] += block_sums[i / SCAN_CHUNK];
 }
 
-__global__ void grid_scatter_kernel(const DevLightVertex* cache, const GridParams* gp, int* cells, unsigned, DevPhoton* photons) {
+__global__ void grid_scatter_kernel(const DevLightVertex* cache, const GridParams* gp, int* cells, unsigned, DevPhoton* photons, float4* photon_pos) {
     const GridParams g = *gp; const unsigned table = g.table;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= g.count) return;
@@ -369,11 +369,11 @@ __global__ void grid_scatter_kernel(const DevLightVertex* cache, const GridParam
     p.pos_dvcm = make_float4(v.pos_len.x, v.pos_len.y, v.pos_len.z, v.gn_dvcm.w);
     p.dir_dvm = make_float4(v.out_mat.x, v.out_mat.y, v.out_mat.z, v.ut_dvm.w);
     p.thr = make_float4(v.thr_v.x, v.thr_v.y, v.thr_v.z, 0.0f);
-    photons[slot] = p;
+    photons[slot] = p; photon_pos[slot] = p.pos_dvcm;
 }
 
 /* HashGrid::query (rangesearch.h:78-129): k nearest photons within the radius; returns their indices sorted by distance */
-__device__ __forceinline__ int grid_query(const GridParams& g, const int* cells, unsigned table, const DevPhoton* photons, V3 q, int k, int* out, float* dist) {
+__device__ __forceinline__ int grid_query(const GridParams& g, const int* cells, unsigned table, const float4* photon_pos, V3 q, int k, int* out, float* dist) {
     if (!(q.x >= g.lo[0] && q.x <= g.hi[0] && q.y >= g.lo[1] && q.y <= g.hi[1] && q.z >= g.lo[2] && q.z <= g.hi[2])) return 0;
     const V3 cell = g.inv_cell_size * (q - v3(g.lo[0], g.lo[1], g.lo[2]));
     const V3 coord = v3(floorf(cell.x), floorf(cell.y), floorf(cell.z));
@@ -386,7 +386,7 @@ __device__ __forceinline__ int grid_query(const GridParams& g, const int* cells,
         int b = c == 0 ? 0 : cells[c - 1];
         const int e = cells[c];
         for (; b < e; ++b) {
-            const float4 pp = __ldg(&photons[b].pos_dvcm);
+            const float4 pp = __ldg(photon_pos + b);
             const V3 d = q - v3(pp);
             const float dist_sqr = dot(d, d);
             if (dist_sqr <= g.radius_sqr) {
@@ -426,12 +426,81 @@ __global__ void vcm_camera_raygen_kernel(DevCamera cam, const VcmParams* Pd, int
     states[i] = st;
 }
 
+/* grid_query for a compile-time k with the candidate list in registers: same visiting order, same insertion rule (a new
+ * candidate goes behind entries of equal distance; a full list takes it if it is not farther than the last entry), so the
+ * result is the list grid_query returns -- without the local-memory traffic of the dynamically indexed insertion sort, which
+ * was 60 % of the stall samples of this pass (ncu, stilllife-proxy: ~430 photons scanned and ~40 insertions per query). */
+template <int K>
+__device__ __forceinline__ int grid_query_fixed(const GridParams& g, const int* cells, unsigned table, const float4* photon_pos, V3 q, int* out) {
+    if (!(q.x >= g.lo[0] && q.x <= g.hi[0] && q.y >= g.lo[1] && q.y <= g.hi[1] && q.z >= g.lo[2] && q.z <= g.hi[2])) return 0;
+    const V3 cell = g.inv_cell_size * (q - v3(g.lo[0], g.lo[1], g.lo[2]));
+    const V3 coord = v3(floorf(cell.x), floorf(cell.y), floorf(cell.z));
+    const int px = (int)coord.x, py = (int)coord.y, pz = (int)coord.z;
+    const V3 fr = cell - coord;
+    const int pxo = px + (fr.x < 0.5f ? -1 : 1), pyo = py + (fr.y < 0.5f ? -1 : 1), pzo = pz + (fr.z < 0.5f ? -1 : 1);
+    float dist[K]; int idx[K];
+#pragma unroll
+    for (int l = 0; l < K; ++l) { dist[l] = FLT_MAX; idx[l] = -1; }   // unused slots: farther than anything inside the radius
+    int count = 0;
+    for (int j = 0; j < 8; ++j) {
+        const unsigned c = cell_hash((unsigned)((j & 4) ? pxo : px), (unsigned)((j & 2) ? pyo : py), (unsigned)((j & 1) ? pzo : pz), table);
+        int b = c == 0 ? 0 : cells[c - 1];
+        const int e = cells[c];
+        for (; b < e; ++b) {
+            const float4 pp = __ldg(photon_pos + b);
+            const V3 d = q - v3(pp);
+            const float ds = dot(d, d);
+            if (ds <= g.radius_sqr && !(dist[K - 1] < ds)) {
+                if (count < K) ++count;
+                bool placed = false;
+#pragma unroll
+                for (int l = K - 1; l >= 1; --l) {
+                    if (dist[l - 1] > ds) { dist[l] = dist[l - 1]; idx[l] = idx[l - 1]; }
+                    else if (!placed) { dist[l] = ds; idx[l] = b; placed = true; }
+                }
+                if (!placed) { dist[0] = ds; idx[0] = b; }
+            }
+        }
+    }
+#pragma unroll
+    for (int l = 0; l < K; ++l) if (l < count) out[l] = idx[l];
+    return count;
+}
+
+/* k-NN search of the camera wavefront as its own pass: light on registers (full occupancy hides the latency of the scattered
+ * cell reads), streaming through 16-byte positions; the shading kernel picks the lists up.  Searches are issued for every hit on
+ * a non-specular, non-emitting material below the length cap -- a superset of the vertices that merge (vcm.cpp:572-611). */
+__global__ void __launch_bounds__(256) vcm_merge_query_kernel(const DeviceShading S, const VcmParams* Pd, const float4* rays, const int4* hits, const VCMState* states,
+                                                              const int* sorted, const int* hit_count_ptr, const GridParams* gp, const int* cells,
+                                                              const float4* photon_pos, int* found_out, int stride) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= *hit_count_ptr) return;
+    const int idx = sorted[i];
+    const int4 h = hits[idx];
+    const int mat = __ldg(S.indices + h.x).w;   // hits carry global triangle ids (= mesh_tri_base[mesh] + local id, as calc_intersection resolves them)
+    const float4 mh = __ldg(S.materials + 5 * mat);
+    const int kind = __float_as_int(mh.x);
+    const int path_length = (int)(states[idx].len_finite & 0x7fffffffu);
+    int count = 0;
+    const int k = Pd->num_knn;
+    int found[IMBA_MAX_KNN]; float dist[IMBA_MAX_KNN];
+    if (__float_as_int(mh.w) == 0 && kind != MAT_MIRROR && kind != MAT_GLASS && path_length < Pd->max_path_len) {
+        const float4 ro = rays[2 * idx], rd = rays[2 * idx + 1];
+        const V3 pos = v3(ro) + __int_as_float(h.z) * v3(rd);      // calc_intersection: pos = org + t * dir
+        const GridParams g = *gp;
+        count = k == 10 ? grid_query_fixed<10>(g, cells, g.table, photon_pos, pos, found)      // the reference's default (cmd_line.h)
+                        : grid_query(g, cells, g.table, photon_pos, pos, k, found, dist);
+    }
+    found_out[idx] = count;
+    for (int j = 0; j < count; ++j) found_out[(size_t)(j + 1) * stride + idx] = found[j];
+}
+
 template <int ALGO>
 __global__ void __launch_bounds__(128) vcm_camera_shade_kernel(const DeviceShading S, const VcmParams* Pd, float4* rays, const int4* hits, VCMState* states, const int* sorted,
                                                                const int* hit_count_ptr, const int* queue_count_ptr, float4* shadow_rays, ShadowState* shadow_states,
                                                                const DevLightVertex* cache, const GridParams* gp, const int* cells, unsigned table,
-                                                               const DevPhoton* photons, float* fb, unsigned long long* ray_stats, float4* out_rays, VCMState* out_states,
-                                                               int* out_count) {
+                                                               const DevPhoton* photons, const int* merge_found, int merge_stride, float* fb, unsigned long long* ray_stats,
+                                                               float4* out_rays, VCMState* out_states, int* out_count) {
     const VcmParams P = *Pd;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i == 0 && ray_stats) atomicAdd(ray_stats, (unsigned long long)*queue_count_ptr);
@@ -523,13 +592,14 @@ __global__ void __launch_bounds__(128) vcm_camera_shade_kernel(const DeviceShadi
         }
     }
     if (ALGO != IMBA_ALGO_BPT && ALGO != IMBA_ALGO_VCM_PT && !bsdf.is_specular()) { // vertex_merging (vcm.cpp:572-611)
-        int found[IMBA_MAX_KNN]; float dist[IMBA_MAX_KNN];
+        // the k nearest photons were found by vcm_merge_query_kernel (sorted by distance, nearest first)
         const int k = P.num_knn;
-        const int count = grid_query(g, cells, g.table, photons, is.pos, k, found, dist);
-        const float radius_sqr = (count == k) ? dist[k - 1] : (P.pm_radius * P.pm_radius);
+        const int count = merge_found[idx];
+        float radius_sqr = P.pm_radius * P.pm_radius;
+        if (count == k) { const V3 dk = is.pos - v3(photons[merge_found[(size_t)k * merge_stride + idx]].pos_dvcm); radius_sqr = dot(dk, dk); }
         V3 contrib = v3(0.0f);
         for (int j = 0; j < count; ++j) {
-            const DevPhoton p = photons[found[j]];
+            const DevPhoton p = photons[merge_found[(size_t)(j + 1) * merge_stride + idx]];
             const V3 in_dir = v3(p.dir_dvm);
             const V3 bsdf_value = bsdf.eval(is.out_dir, in_dir);
             const float pdf_dir_w = bsdf.pdf(is.out_dir, in_dir), pdf_rev_w = bsdf.pdf(in_dir, is.out_dir);
@@ -582,8 +652,12 @@ template <int ALGO>
 cudaError_t camera_shade(const VcmLaunch& a, cudaStream_t st) {
     if (a.S->env_tex >= 0 && ALGO != IMBA_ALGO_VCM_PT)
         vcm_camera_miss_kernel<ALGO><<<(a.capacity + 255) / 256, 256, 0, st>>>(*a.S, a.rays, a.states, a.sorted, a.hit_count_ptr, a.queue_count_ptr, a.fb);
+    if (ALGO == IMBA_ALGO_VCM || ALGO == IMBA_ALGO_PPM)
+        vcm_merge_query_kernel<<<(a.capacity + 255) / 256, 256, 0, st>>>(*a.S, a.P, a.rays, a.hits, a.states, a.sorted, a.hit_count_ptr, a.grid, a.cells, a.photon_pos,
+                                                                       a.merge_found, a.merge_stride);
     vcm_camera_shade_kernel<ALGO><<<(a.capacity + 127) / 128, 128, 0, st>>>(*a.S, a.P, a.rays, a.hits, a.states, a.sorted, a.hit_count_ptr, a.queue_count_ptr, a.shadow_rays,
-                                                                           a.shadow_states, a.cache, a.grid, a.cells, a.table, a.photons, a.fb, a.ray_stats, a.out_rays, a.out_states, a.out_count);
+                                                                           a.shadow_states, a.cache, a.grid, a.cells, a.table, a.photons, a.merge_found, a.merge_stride, a.fb,
+                                                                           a.ray_stats, a.out_rays, a.out_states, a.out_count);
     return cudaGetLastError();
 }
 
@@ -641,7 +715,7 @@ cudaError_t imba_vcm_light_tail(int algo, bool masks, const VcmLaunch& a, const 
 
 /* HashGrid::build on the vertex cache; `cells` has `table` + 1 ints, block_sums (table / 2048 + 1) ints */
 cudaError_t imba_grid_build(const DevLightVertex* cache, const int* cache_last, int cache_capacity, float radius, GridParams* grid, int* bbox, int* cells, unsigned table,
-                            int* block_sums, DevPhoton* photons, bool build_cells, cudaStream_t st) {
+                            int* block_sums, DevPhoton* photons, float4* photon_pos, bool build_cells, cudaStream_t st) {
     static const int init_bbox[6] = { 0x7f7fffff, 0x7f7fffff, 0x7f7fffff, (int)(0xff7fffffu ^ 0x7fffffffu), (int)(0xff7fffffu ^ 0x7fffffffu), (int)(0xff7fffffu ^ 0x7fffffffu) };
     cudaError_t e = cudaMemcpyAsync(bbox, init_bbox, sizeof(init_bbox), cudaMemcpyHostToDevice, st);
     if (e != cudaSuccess) return e;
@@ -655,7 +729,7 @@ cudaError_t imba_grid_build(const DevLightVertex* cache, const int* cache_last, 
         scan_local_kernel<<<nchunks, 256, 0, st>>>(cells, (int)table, block_sums);
         scan_sums_kernel<<<1, 1024, 0, st>>>(block_sums, nchunks);
         scan_add_kernel<<<((int)table + 255) / 256, 256, 0, st>>>(cells, (int)table, block_sums);
-        grid_scatter_kernel<<<blocks, 256, 0, st>>>(cache, grid, cells, table, photons);
+        grid_scatter_kernel<<<blocks, 256, 0, st>>>(cache, grid, cells, table, photons, photon_pos);
     }
     return cudaGetLastError();
 }

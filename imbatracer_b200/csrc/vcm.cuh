@@ -21,6 +21,9 @@ struct VcmLaunch {
     float4* shadow_rays; ShadowState* shadow_states;
     DevLightVertex* cache; int cache_capacity; int* cache_last;
     const GridParams* grid; const int* cells; unsigned table; const DevPhoton* photons;
+    const float4* photon_pos;   // positions only, in cell order: what the k-NN search streams through
+    int* merge_found;           // k-NN results per queue slot: row 0 = count, rows 1..k = photon indices; row stride = merge_stride
+    int merge_stride;
     float* fb; unsigned long long* ray_stats;
     float4* out_rays; VCMState* out_states; int* out_count; // next wavefront's queue (fused compaction)
 };
@@ -31,5 +34,5 @@ cudaError_t imba_vcm_light_shade(int algo, const VcmLaunch& a, cudaStream_t st);
 cudaError_t imba_vcm_camera_shade(int algo, const VcmLaunch& a, cudaStream_t st);
 cudaError_t imba_vcm_light_tail(int algo, bool masks, const VcmLaunch& a, const TraceArgs& T, int capacity, cudaStream_t st);
 cudaError_t imba_grid_build(const DevLightVertex* cache, const int* cache_last, int cache_capacity, float radius, GridParams* grid, int* bbox, int* cells, unsigned table,
-                            int* block_sums, DevPhoton* photons, bool build_cells, cudaStream_t st);
+                            int* block_sums, DevPhoton* photons, float4* photon_pos, bool build_cells, cudaStream_t st);
 #endif

@@ -6,6 +6,8 @@
  * have no length cap (only Russian roulette ends them, vcm.cpp:133-139), so the host reads the queue size back after
  * every wavefront of the light pass.  The camera pass is capped by max_path_len and is enqueued without host sync.
  */
+#include <algorithm>
+#include <vector>
 #include "vcm.cuh"
 #include <cstdlib>
 
@@ -33,6 +35,7 @@ static VcmLaunch base_launch(imba_integrator* it, int cur, int capacity) {
     a.shadow_rays = it->shadow_rays; a.shadow_states = it->shadow_states;
     a.cache = it->cache; a.cache_capacity = it->cache_capacity; a.cache_last = it->cache_last;
     a.grid = it->grid; a.cells = it->cells; a.table = it->table; a.photons = it->photons;
+    a.photon_pos = it->photon_pos; a.merge_found = it->merge_found; a.merge_stride = it->capacity;
     a.fb = it->fb; a.ray_stats = it->d_stats;
     a.out_rays = it->rays[cur ^ 1]; a.out_states = (VCMState*)it->states[cur ^ 1]; a.out_count = it->count[cur ^ 1];
     return a;
@@ -138,6 +141,7 @@ void imba_vcm_free(imba_integrator* it) {
     for (int i = 0; i < imba_integrator::kParkedGraphs; ++i) if (it->parked_graph[i]) { cudaGraphExecDestroy(it->parked_graph[i]); it->parked_graph[i] = nullptr; }
     cudaFree(it->d_params); it->d_params = nullptr; cudaFree(it->tail_counters); it->tail_counters = nullptr;
     cudaFree(it->cache); cudaFree(it->cache_last); cudaFree(it->grid); cudaFree(it->grid_bbox); cudaFree(it->cells); cudaFree(it->block_sums); cudaFree(it->photons);
+    cudaFree(it->photon_pos); cudaFree(it->merge_found); it->photon_pos = nullptr; it->merge_found = nullptr;
     it->cache = nullptr; it->cache_last = nullptr; it->grid = nullptr; it->grid_bbox = nullptr; it->cells = nullptr; it->block_sums = nullptr; it->photons = nullptr;
 }
 
@@ -153,6 +157,8 @@ int imba_vcm_allocate(imba_integrator* it) {
     ok = ok && cudaMalloc((void**)&it->cells, sizeof(int) * ((size_t)it->table + 1)) == cudaSuccess;
     ok = ok && cudaMalloc((void**)&it->block_sums, sizeof(int) * ((size_t)it->table / 2048 + 2)) == cudaSuccess;
     ok = ok && cudaMalloc((void**)&it->photons, (size_t)cap * sizeof(DevPhoton)) == cudaSuccess;
+    ok = ok && cudaMalloc((void**)&it->photon_pos, (size_t)cap * sizeof(float4)) == cudaSuccess;
+    ok = ok && cudaMalloc((void**)&it->merge_found, (size_t)(IMBA_MAX_KNN + 1) * std::max(it->capacity, 1) * sizeof(int)) == cudaSuccess;
     if (!ok) { imba_set_error("VCM allocation failed: %s", cudaGetErrorString(cudaGetLastError())); return IMBA_ERR_CUDA; }
     return IMBA_OK;
 }
@@ -205,8 +211,18 @@ int imba_vcm_render_iteration(imba_integrator* it) {
         if (rc != IMBA_OK) return rc;
         if (algo != IMBA_ALGO_LT) { // light_vertices_.build(pm_radius_, algo != ALGO_BPT), vcm.cpp:98-99
             IMBA_CUDA(imba_grid_build(it->cache, it->cache_last, it->cache_capacity, P.pm_radius, it->grid, it->grid_bbox, it->cells, it->table, it->block_sums,
-                                      it->photons, algo != IMBA_ALGO_BPT, it->stream), IMBA_ERR_CUDA);
+                                      it->photons, it->photon_pos, algo != IMBA_ALGO_BPT, it->stream), IMBA_ERR_CUDA);
             g_imba_launches.fetch_add(algo != IMBA_ALGO_BPT ? 7 : 1);
+            if (getenv("IMBA_GRID_STATS") && algo != IMBA_ALGO_BPT) { // occupancy of the photon hash grid (diagnosis only)
+                GridParams g; cudaMemcpy(&g, it->grid, sizeof(g), cudaMemcpyDeviceToHost);
+                std::vector<int> ends(g.table);
+                cudaMemcpy(ends.data(), it->cells, sizeof(int) * g.table, cudaMemcpyDeviceToHost);
+                long long used = 0, sq = 0; int mx = 0, prev = 0; std::vector<int> sizes;
+                for (unsigned c = 0; c < g.table; ++c) { const int n = ends[c] - prev; prev = ends[c]; if (n > 0) { ++used; sq += (long long)n * n; mx = std::max(mx, n); sizes.push_back(n); } }
+                std::sort(sizes.begin(), sizes.end());
+                fprintf(stderr, "[imba] photon grid: %d photons, table %u, %lld cells used, largest %d, median %d, p99 %d, mean photons scanned per visited photon's cell %.1f, radius %g\n",
+                        g.count, g.table, used, mx, sizes.empty() ? 0 : sizes[sizes.size() / 2], sizes.empty() ? 0 : sizes[sizes.size() * 99 / 100], g.count ? (double)sq / g.count : 0.0, sqrt(g.radius_sqr));
+            }
         }
     }
     if (algo != IMBA_ALGO_LT) {
@@ -256,7 +272,7 @@ extern "C" int imba_vcm_stage_batch(imba_integrator* it, int stage, int iteratio
         IMBA_CUDA(cudaMemcpyAsync(it->cache_last, &cache_in_count, 4, cudaMemcpyHostToDevice, st), IMBA_ERR_CUDA);
         IMBA_CUDA(cudaStreamSynchronize(st), IMBA_ERR_CUDA);
         IMBA_CUDA(imba_grid_build(it->cache, it->cache_last, it->cache_capacity, P.pm_radius, it->grid, it->grid_bbox, it->cells, it->table, it->block_sums,
-                                  it->photons, algo != IMBA_ALGO_BPT && algo != IMBA_ALGO_VCM_PT, st), IMBA_ERR_CUDA);
+                                  it->photons, it->photon_pos, algo != IMBA_ALGO_BPT && algo != IMBA_ALGO_VCM_PT, st), IMBA_ERR_CUDA);
     }
     IMBA_CUDA(imba_sort_hits_by_material(it->part, it->hits, S.indices, S.material_count, (int*)it->shadow_states, slots, it->count[0], 0, count, st), IMBA_ERR_CUDA);
     VcmLaunch a = base_launch(it, 0, count);
