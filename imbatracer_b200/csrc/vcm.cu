@@ -266,14 +266,28 @@ __global__ void __launch_bounds__(128) vcm_light_tail_warp_kernel(const DeviceSh
 __device__ __forceinline__ int ordered_int(float f) { const int i = __float_as_int(f); return i >= 0 ? i : i ^ 0x7fffffff; }
 __device__ __forceinline__ float from_ordered(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
 
-__global__ void grid_bbox_kernel(const DevLightVertex* cache, const int* last, int capacity, int* bbox /* 6 ordered ints */) {
+__global__ void __launch_bounds__(256) grid_bbox_kernel(const DevLightVertex* cache, const int* last, int capacity, int* bbox /* 6 ordered ints */) {
+    // grid-stride over the vertices, then warp and block reductions: 6 atomics per BLOCK (one per warp made 1.6 M atomics on six
+    // addresses out of 8.8 M vertices: 1.7 ms)
+    __shared__ float red[6][8];
     const int n = min(*last, capacity);
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
     float lo[3] = { FLT_MAX, FLT_MAX, FLT_MAX }, hi[3] = { -FLT_MAX, -FLT_MAX, -FLT_MAX };
-    if (i < n) { const float4 p = cache[i].pos_len; lo[0] = hi[0] = p.x; lo[1] = hi[1] = p.y; lo[2] = hi[2] = p.z; }
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float4 p = cache[i].pos_len;
+        lo[0] = fminf(lo[0], p.x); lo[1] = fminf(lo[1], p.y); lo[2] = fminf(lo[2], p.z);
+        hi[0] = fmaxf(hi[0], p.x); hi[1] = fmaxf(hi[1], p.y); hi[2] = fmaxf(hi[2], p.z);
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int a = 0; a < 3; ++a) {
         for (int o = 16; o > 0; o >>= 1) { lo[a] = fminf(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], o)); hi[a] = fmaxf(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], o)); }
-        if ((threadIdx.x & 31) == 0) { atomicMin(bbox + a, ordered_int(lo[a])); atomicMax(bbox + 3 + a, ordered_int(hi[a])); }
+        if (lane == 0) { red[a][warp] = lo[a]; red[3 + a][warp] = hi[a]; }
+    }
+    __syncthreads();
+    if (threadIdx.x < 6) {
+        float v = red[threadIdx.x][0];
+        for (int w = 1; w < 8; ++w) v = threadIdx.x < 3 ? fminf(v, red[threadIdx.x][w]) : fmaxf(v, red[threadIdx.x][w]);
+        if (threadIdx.x < 3) { if (v != FLT_MAX) atomicMin(bbox + threadIdx.x, ordered_int(v)); }
+        else if (v != -FLT_MAX) atomicMax(bbox + threadIdx.x, ordered_int(v));
     }
 }
 
@@ -720,7 +734,7 @@ cudaError_t imba_grid_build(const DevLightVertex* cache, const int* cache_last, 
     cudaError_t e = cudaMemcpyAsync(bbox, init_bbox, sizeof(init_bbox), cudaMemcpyHostToDevice, st);
     if (e != cudaSuccess) return e;
     const int blocks = (std::max(cache_capacity, 1) + 255) / 256;
-    if (build_cells) grid_bbox_kernel<<<blocks, 256, 0, st>>>(cache, cache_last, cache_capacity, bbox);
+    if (build_cells) grid_bbox_kernel<<<std::min(blocks, 148 * 8), 256, 0, st>>>(cache, cache_last, cache_capacity, bbox);
     grid_prepare_kernel<<<1, 1, 0, st>>>(bbox, cache_last, cache_capacity, grid, radius);
     if (build_cells) {
         if ((e = cudaMemsetAsync(cells, 0, sizeof(int) * (size_t)(table + 1), st)) != cudaSuccess) return e;
