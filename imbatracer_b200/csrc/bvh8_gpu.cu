@@ -276,8 +276,7 @@ int imba_scene_build_accel_device(imba_scene* s, const imba_scene_desc* d, float
         LbvhTree t; DeviceBuf F, dec, ptot, flags2;
         BG_CUDA(F.alloc((size_t)(2 * n) * 7 * 4)); BG_CUDA(dec.alloc((size_t)n * 4)); BG_CUDA(ptot.alloc((size_t)2 * n)); BG_CUDA(flags2.alloc((size_t)n * 4));
         BG_CUDA(cudaMemset(flags2.p, 0, (size_t)n * 4));
-        cudaEventRecord(e0);
-        BG_CUDA(use_ploc ? ploc_build_tree(m, t) : lbvh_build_tree(m, t));
+        BG_CUDA(use_ploc ? ploc_build_tree(m, t, e0) : lbvh_build_tree(m, t, e0));
         CostTables T{ F.as<float>(), dec.as<uint32_t>(), ptot.as<uint8_t>() };
         const int blocks = (n + 255) / 256;
         collapse_cost_kernel<<<blocks, 256>>>(n, t.kids(), t.parents(), t.bounds(), flags2.as<int>(), T, cost_prim);

@@ -65,8 +65,7 @@ extern "C" imba_accel* imba_accel_build_gpu(const imba_scene_desc* d, float* out
         LbvhTree t; DeviceBuf d_nodes, d_tris;
         LB_CUDA(d_nodes.alloc((size_t)std::max(n - 1, 1) * sizeof(imba_node2))); LB_CUDA(d_tris.alloc((size_t)n * 48));
         const int blocks = (n + 255) / 256;
-        cudaEventRecord(e0);
-        LB_CUDA(use_ploc ? ploc_build_tree(m, t) : lbvh_build_tree(m, t));
+        LB_CUDA(use_ploc ? ploc_build_tree(m, t, e0) : lbvh_build_tree(m, t, e0));
         lbvh_emit_kernel<<<blocks, 256>>>(m, t.sorted_ids(), n, t.kids(), t.bounds(), node_base, vec4_base, d_nodes.as<imba_node2>(), d_tris.as<float4>());
         cudaEventRecord(e1);
         LB_CUDA(cudaGetLastError());

@@ -135,7 +135,7 @@ struct LbvhTree {
 };
 
 /* Allocates the buffers and enqueues the build of mesh `m` on the default stream (5 launches incl. the sort, 3 when n == 1). */
-inline cudaError_t lbvh_build_tree(const MeshView& m, LbvhTree& t) {
+inline cudaError_t lbvh_build_tree(const MeshView& m, LbvhTree& t, cudaEvent_t after_alloc = nullptr) {
     const int n = m.nt; t.n = n;
     cudaError_t e;
 #define LBT(x) do { if ((e = (x)) != cudaSuccess) return e; } while (0)
@@ -148,6 +148,7 @@ inline cudaError_t lbvh_build_tree(const MeshView& m, LbvhTree& t) {
     LBT(cudaMemcpy(t.bbox.p, init_bbox, sizeof(init_bbox), cudaMemcpyHostToDevice));
     LBT(cudaMemset(t.flags.p, 0, (size_t)n * 4));
     const int blocks = (n + 255) / 256;
+    if (after_alloc) cudaEventRecord(after_alloc);   // device time is measured from here: cudaMalloc is host work
     lbvh_bounds_kernel<<<blocks, 256>>>(m, t.bbox.as<int>());
     lbvh_morton_kernel<<<blocks, 256>>>(m, t.bbox.as<int>(), t.keys.as<unsigned long long>(), t.ids.as<int>());
     LBT(cub::DeviceRadixSort::SortPairs(t.temp.p, temp_bytes, t.keys.as<unsigned long long>(), t.keys2.as<unsigned long long>(), t.ids.as<int>(), t.ids2.as<int>(), n, 0, 63));
@@ -227,7 +228,7 @@ __global__ void ploc_merge_kernel(const int* cid, int count, const int* nearest,
 struct PlocValid { __device__ __forceinline__ bool operator()(const int& x) const { return x >= 0; } };
 
 /* Same contract as lbvh_build_tree; t.root is the id of the last merge. */
-inline cudaError_t ploc_build_tree(const MeshView& m, LbvhTree& t) {
+inline cudaError_t ploc_build_tree(const MeshView& m, LbvhTree& t, cudaEvent_t after_alloc = nullptr) {
     const int n = m.nt; t.n = n;
     cudaError_t e;
 #define LBT(x) do { if ((e = (x)) != cudaSuccess) return e; } while (0)
@@ -245,6 +246,7 @@ inline cudaError_t ploc_build_tree(const MeshView& m, LbvhTree& t) {
     LBT(cudaMemset(counters.p, 0, 16));
     LBT(cudaMemset(t.parent.p, 0xff, (size_t)(2 * n) * 4));
     const int blocks = (n + 255) / 256;
+    if (after_alloc) cudaEventRecord(after_alloc);   // device time is measured from here: cudaMalloc is host work
     lbvh_bounds_kernel<<<blocks, 256>>>(m, t.bbox.as<int>());
     lbvh_morton_kernel<<<blocks, 256>>>(m, t.bbox.as<int>(), t.keys.as<unsigned long long>(), t.ids.as<int>());
     LBT(cub::DeviceRadixSort::SortPairs(t.temp.p, temp_bytes, t.keys.as<unsigned long long>(), t.keys2.as<unsigned long long>(), t.ids.as<int>(), t.ids2.as<int>(), n, 0, 63));
