@@ -29,10 +29,12 @@ constexpr int      REFILL_LANES = 20; // refill when fewer lanes than this are a
 /* MODE 0 = closest hit, 1 = any hit, 2 = any hit fused with process_shadow_rays (integrator.h:49-63): no hit record is
  * written; an unoccluded ray adds its ShadowState throughput to the accumulation buffer; slots whose pixel_id < 0 are skipped. */
 template <int MODE, bool MASKS, bool STATS>
-#ifndef IMBA_MIN_BLOCKS
-#define IMBA_MIN_BLOCKS 1
-#endif
+// (an explicit minimum of 1 block per SM makes ptxas spend 92-96 registers; leaving it open gives 56 and 9 resident blocks)
+#ifdef IMBA_MIN_BLOCKS
 __global__ void __launch_bounds__(BLOCK_THREADS, IMBA_MIN_BLOCKS) trace_kernel(const TraceArgs P) {
+#else
+__global__ void __launch_bounds__(BLOCK_THREADS) trace_kernel(const TraceArgs P) {
+#endif
     constexpr bool ANY = MODE != 0;
     constexpr bool RESOLVE = MODE == 2;
     const int ray_count = P.count_ptr ? *P.count_ptr * P.count_mul : P.count;
