@@ -67,3 +67,19 @@ def test_cpp_host_mirror_compiles_links_and_refuses_without_gpu(tmp_path):
                     "-o", exe, "-L", lib_dir, "-limba_b200", f"-Wl,-rpath,{lib_dir}"], check=True)
     r = subprocess.run([exe], stdout=subprocess.PIPE, text=True)
     assert r.returncode in (0, 2), (r.returncode, r.stdout)
+
+
+def test_traversal_kernel_resource_budget():
+    """The persistent traversal kernel is tuned for 56 registers (9 resident blocks of 128 threads per SM) and no spills;
+    ptxas writes its resource usage to the build log.  A change that silently pushes it to 90+ registers halves occupancy."""
+    import os
+    import re
+    log = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "imbatracer_b200", "csrc", "build", "traverse.ptxas.log")
+    if not os.path.exists(log):
+        import pytest
+        pytest.skip("library was not built in this tree")
+    text = open(log).read()
+    regs = [int(x) for x in re.findall(r"Used (\d+) registers", text)]
+    spills = [int(x) for x in re.findall(r"(\d+) bytes spill stores", text)]
+    assert regs and max(regs) <= 64, regs
+    assert max(spills) == 0, spills
