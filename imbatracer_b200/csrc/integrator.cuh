@@ -103,7 +103,7 @@ __device__ __forceinline__ int queue_push_slot(int* count) {
     base = __shfl_sync(m, base, leader);
     return base + __popc(m & ((1u << lane) - 1u));
 }
-cudaError_t imba_pt_miss(const DeviceShading& S, const float4* rays, const PTState* states, const int* sorted, const int* hit_count_ptr, const int* queue_count_ptr,
+cudaError_t imba_pt_miss(const DeviceShading& S, const float4* rays, const int4* hits, const PTState* states, const int* sorted, const int* hit_count_ptr, const int* queue_count_ptr,
                          int capacity, float* fb, cudaStream_t st);
 cudaError_t imba_probe_raygen(const DevCamera& cam, float4* rays, int count, cudaStream_t st);
 cudaError_t imba_probe_reduce(const float4* rays, const int4* hits, int quads, float* total, int* count, cudaStream_t st);

@@ -39,12 +39,18 @@ __global__ void __launch_bounds__(128) pt_shade_kernel(const DeviceShading S, fl
                                                        float* fb, int max_path_len, unsigned long long* ray_stats, float4* out_rays, PTState* out_states,
                                                        int* out_count) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const int hit_count = *hit_count_ptr;
     if (i == 0 && ray_stats) atomicAdd(ray_stats, (unsigned long long)*queue_count_ptr); // rays traced in this wavefront (tile_scheduler.h:117-127)
-    if (i >= hit_count) return;
-    const int idx = sorted[i];
-    const float4 ro = rays[2 * idx], rd = rays[2 * idx + 1];
+    // sorted != null: the reference's order (compact_hits + sort_by_material, pt.cpp:85-93), hits only.  sorted == null: queue
+    // order, every slot -- the integrator's default: the per-path results are the same, and on the GPU the sort costs more
+    // (14 % of an iteration) than the divergence between four material kinds it removes.
+    if (i >= (sorted ? *hit_count_ptr : *queue_count_ptr)) return;
+    const int idx = sorted ? sorted[i] : i;
     const int4 h = hits[idx];
+    if (!sorted) {
+        shadow_states[idx].pixel_id = -1;             // what the sort pass does for every slot: no shadow ray yet
+        if (h.x < 0) { states[idx].pixel_id = -1; return; }
+    }
+    const float4 ro = rays[2 * idx], rd = rays[2 * idx + 1];
     PTState st = states[idx];
     const float t = __int_as_float(h.z);
     const Isect is = calc_intersection(S, ro, rd, h.x, h.y, t, __int_as_float(h.w));
@@ -121,11 +127,12 @@ __global__ void __launch_bounds__(128) pt_shade_kernel(const DeviceShading S, fl
 }
 
 /* Rays that left the scene pick up the environment map (pt.cpp:95-116); misses are the last bin of the material sort. */
-__global__ void pt_miss_kernel(const DeviceShading S, const float4* rays, const PTState* states, const int* sorted, const int* hit_count_ptr,
+__global__ void pt_miss_kernel(const DeviceShading S, const float4* rays, const int4* hits, const PTState* states, const int* sorted, const int* hit_count_ptr,
                                const int* queue_count_ptr, float* fb) {
-    const int i = *hit_count_ptr + blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = (sorted ? *hit_count_ptr : 0) + blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= *queue_count_ptr) return;
-    const int idx = sorted[i];
+    const int idx = sorted ? sorted[i] : i;
+    if (!sorted && hits[idx].x >= 0) return;          // queue order: pick the misses out
     const PTState st = states[idx];
     const V3 out_dir = normalize(v3(rays[2 * idx + 1]));
     float pdf_direct_w, pdf_emit_w;
@@ -183,10 +190,10 @@ cudaError_t imba_pt_shade(const DeviceShading& S, float4* rays, const int4* hits
     return cudaGetLastError();
 }
 
-cudaError_t imba_pt_miss(const DeviceShading& S, const float4* rays, const PTState* states, const int* sorted, const int* hit_count_ptr, const int* queue_count_ptr,
-                         int capacity, float* fb, cudaStream_t st) {
+cudaError_t imba_pt_miss(const DeviceShading& S, const float4* rays, const int4* hits, const PTState* states, const int* sorted, const int* hit_count_ptr,
+                         const int* queue_count_ptr, int capacity, float* fb, cudaStream_t st) {
     if (capacity <= 0 || S.env_tex < 0) return cudaSuccess;
-    pt_miss_kernel<<<(capacity + 255) / 256, 256, 0, st>>>(S, rays, states, sorted, hit_count_ptr, queue_count_ptr, fb);
+    pt_miss_kernel<<<(capacity + 255) / 256, 256, 0, st>>>(S, rays, hits, states, sorted, hit_count_ptr, queue_count_ptr, fb);
     return cudaGetLastError();
 }
 

@@ -60,3 +60,38 @@ def test_warp_per_path_tail_equals_thread_per_path_tail(algo, monkeypatch):
         assert counts == out[0][1], (counts, out[0][1])
         assert abs(img.sum() - out[0][0].sum()) <= 2e-4 * out[0][0].sum()
         assert np.abs(img - out[0][0]).max() <= 1e-3 * max(1.0, out[0][0].max())
+
+
+@pytest.mark.parametrize("envmap", [False, True])
+def test_queue_order_shading_equals_material_sorted_shading(envmap, monkeypatch):
+    """The PT integrator shades in queue order by default; IMBA_PT_SORT=1 runs the reference's order of work (compact_hits +
+    sort_by_material before shading, pt.cpp:85-93).  Paths carry their own RNG, so the per-path results are the same: identical
+    ray counts, images equal up to the order of the atomic float adds -- also when misses pick up an environment map."""
+    import os
+    from imbatracer_b200 import api
+    from tests import refapi
+    if envmap:
+        if not (refapi.have_ref() and os.path.isdir(refapi.REF_SCENES)):
+            pytest.skip("oracle/_ref not built")
+        rs = refapi.RefScene(refapi.scene_path("cornell_org"), True)
+        rs.add_test_envmap(5, 0.7)
+        flat = rs.flat("cornell_org_env"); rs.close()
+        flat.cam[:3] = [0.0, 1.0, 6.5]          # step back so that many primary rays miss the box
+    else:
+        flat = load_scene("cornell_specular_front", "gpu")
+    sc = api.Scene(flat)
+    out = []
+    for sort in (False, True):
+        if sort:
+            monkeypatch.setenv("IMBA_PT_SORT", "1")
+        else:
+            monkeypatch.delenv("IMBA_PT_SORT", raising=False)
+        it = api.Integrator(sc, api.render_settings(flat, "pt", 128, 96, seed=4))
+        it.preprocess(); it.render(6)
+        out.append((it.download(), it.ray_counts()))
+        it.close()
+    sc.close()
+    (a, ca), (b, cb) = out
+    assert ca == cb and ca[0] > 128 * 96 * 6
+    assert a.sum() > 0 and abs(a.sum() - b.sum()) <= 2e-4 * a.sum()
+    assert np.abs(a - b).max() <= 1e-3 * max(1.0, a.max())
