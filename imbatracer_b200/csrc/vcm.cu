@@ -164,8 +164,13 @@ __global__ void __launch_bounds__(128) vcm_light_shade_kernel(const DeviceShadin
     const VcmParams P = *Pd;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i == 0 && ray_stats) atomicAdd(ray_stats, (unsigned long long)*queue_count_ptr);
-    if (i >= *hit_count_ptr) return;
-    const int idx = sorted[i];
+    // sorted == null: queue order, every slot (the integrator's default, see pt_shade_kernel); else the reference's sorted hits
+    if (i >= (sorted ? *hit_count_ptr : *queue_count_ptr)) return;
+    const int idx = sorted ? sorted[i] : i;
+    if (!sorted) {
+        shadow_states[idx].pixel_id = -1;
+        if (hits[idx].x < 0) { states[idx].pixel_id = -1; return; }
+    }
     float4 ro = rays[2 * idx], rd = rays[2 * idx + 1];
     VCMState st = states[idx];
     bool has_shadow; float4 sh_o, sh_d; ShadowState ss;
@@ -485,12 +490,13 @@ __device__ __forceinline__ int grid_query_fixed(const GridParams& g, const int* 
  * cell reads), streaming through 16-byte positions; the shading kernel picks the lists up.  Searches are issued for every hit on
  * a non-specular, non-emitting material below the length cap -- a superset of the vertices that merge (vcm.cpp:572-611). */
 __global__ void __launch_bounds__(256) vcm_merge_query_kernel(const DeviceShading S, const VcmParams* Pd, const float4* rays, const int4* hits, const VCMState* states,
-                                                              const int* sorted, const int* hit_count_ptr, const GridParams* gp, const int* cells,
+                                                              const int* sorted, const int* hit_count_ptr, const int* queue_count_ptr, const GridParams* gp, const int* cells,
                                                               const float4* photon_pos, int* found_out, int stride) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= *hit_count_ptr) return;
-    const int idx = sorted[i];
+    if (i >= (sorted ? *hit_count_ptr : *queue_count_ptr)) return;
+    const int idx = sorted ? sorted[i] : i;
     const int4 h = hits[idx];
+    if (h.x < 0) { found_out[idx] = 0; return; }
     const int mat = __ldg(S.indices + h.x).w;   // hits carry global triangle ids (= mesh_tri_base[mesh] + local id, as calc_intersection resolves them)
     const float4 mh = __ldg(S.materials + 5 * mat);
     const int kind = __float_as_int(mh.x);
@@ -518,11 +524,15 @@ __global__ void __launch_bounds__(128) vcm_camera_shade_kernel(const DeviceShadi
     const VcmParams P = *Pd;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i == 0 && ray_stats) atomicAdd(ray_stats, (unsigned long long)*queue_count_ptr);
-    if (i >= *hit_count_ptr) return;
-    const int idx = sorted[i];
+    if (i >= (sorted ? *hit_count_ptr : *queue_count_ptr)) return;
+    const int idx = sorted ? sorted[i] : i;
     const int slots = P.num_connections + 1;
-    const float4 ro = rays[2 * idx], rd = rays[2 * idx + 1];
     const int4 h = hits[idx];
+    if (!sorted) { // queue order: this kernel sees every slot, also the misses, and resets the shadow slots itself
+        for (int s = 0; s < slots; ++s) shadow_states[(size_t)idx * slots + s].pixel_id = -1;
+        if (h.x < 0) { states[idx].pixel_id = -1; return; }
+    }
+    const float4 ro = rays[2 * idx], rd = rays[2 * idx + 1];
     VCMState st = states[idx];
     const float t = __int_as_float(h.z);
     const Isect is = calc_intersection(S, ro, rd, h.x, h.y, t, __int_as_float(h.w));
@@ -640,11 +650,12 @@ __global__ void __launch_bounds__(128) vcm_camera_shade_kernel(const DeviceShadi
 
 /* Camera paths that leave the scene pick up the environment map (vcm.cpp:345-366); not for the VCM-style PT. */
 template <int ALGO>
-__global__ void vcm_camera_miss_kernel(const DeviceShading S, const float4* rays, const VCMState* states, const int* sorted, const int* hit_count_ptr,
+__global__ void vcm_camera_miss_kernel(const DeviceShading S, const float4* rays, const int4* hits, const VCMState* states, const int* sorted, const int* hit_count_ptr,
                                        const int* queue_count_ptr, float* fb) {
-    const int i = *hit_count_ptr + blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = (sorted ? *hit_count_ptr : 0) + blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= *queue_count_ptr) return;
-    const int idx = sorted[i];
+    const int idx = sorted ? sorted[i] : i;
+    if (!sorted && hits[idx].x >= 0) return;
     const VCMState st = states[idx];
     const V3 out_dir = normalize(v3(rays[2 * idx + 1]));
     float pdf_direct_w, pdf_emit_w;
@@ -665,9 +676,9 @@ cudaError_t light_shade(const VcmLaunch& a, cudaStream_t st) {
 template <int ALGO>
 cudaError_t camera_shade(const VcmLaunch& a, cudaStream_t st) {
     if (a.S->env_tex >= 0 && ALGO != IMBA_ALGO_VCM_PT)
-        vcm_camera_miss_kernel<ALGO><<<(a.capacity + 255) / 256, 256, 0, st>>>(*a.S, a.rays, a.states, a.sorted, a.hit_count_ptr, a.queue_count_ptr, a.fb);
+        vcm_camera_miss_kernel<ALGO><<<(a.capacity + 255) / 256, 256, 0, st>>>(*a.S, a.rays, a.hits, a.states, a.sorted, a.hit_count_ptr, a.queue_count_ptr, a.fb);
     if (ALGO == IMBA_ALGO_VCM || ALGO == IMBA_ALGO_PPM)
-        vcm_merge_query_kernel<<<(a.capacity + 255) / 256, 256, 0, st>>>(*a.S, a.P, a.rays, a.hits, a.states, a.sorted, a.hit_count_ptr, a.grid, a.cells, a.photon_pos,
+        vcm_merge_query_kernel<<<(a.capacity + 255) / 256, 256, 0, st>>>(*a.S, a.P, a.rays, a.hits, a.states, a.sorted, a.hit_count_ptr, a.queue_count_ptr, a.grid, a.cells, a.photon_pos,
                                                                        a.merge_found, a.merge_stride);
     vcm_camera_shade_kernel<ALGO><<<(a.capacity + 127) / 128, 128, 0, st>>>(*a.S, a.P, a.rays, a.hits, a.states, a.sorted, a.hit_count_ptr, a.queue_count_ptr, a.shadow_rays,
                                                                            a.shadow_states, a.cache, a.grid, a.cells, a.table, a.photons, a.merge_found, a.merge_stride, a.fb,

@@ -26,11 +26,11 @@ static VcmParams iteration_params(const imba_integrator* it, uint64_t iteration_
     return P;
 }
 
-static VcmLaunch base_launch(imba_integrator* it, int cur, int capacity) {
+static VcmLaunch base_launch(imba_integrator* it, int cur, int capacity, bool sorted = true) {
     const DeviceShading* S = imba_shading_view(it->scene);
     VcmLaunch a;
     a.S = S; a.P = it->d_params; a.cam = it->cam;
-    a.rays = it->rays[cur]; a.hits = it->hits; a.states = (VCMState*)it->states[cur]; a.sorted = it->part.indices;
+    a.rays = it->rays[cur]; a.hits = it->hits; a.states = (VCMState*)it->states[cur]; a.sorted = sorted ? it->part.indices : nullptr;
     a.hit_count_ptr = it->part.bin_start + S->material_count; a.queue_count_ptr = it->count[cur]; a.capacity = capacity;
     a.shadow_rays = it->shadow_rays; a.shadow_states = it->shadow_states;
     a.cache = it->cache; a.cache_capacity = it->cache_capacity; a.cache_last = it->cache_last;
@@ -49,9 +49,11 @@ static int vcm_wavefront(imba_integrator* it, int algo, bool light, int cur, int
     if (it->tail_counter_next >= 0) rq.d_work_counter = it->tail_counters + it->tail_counter_next++;
     int rc = imba_scene_trace_ex(it->scene, rq, it->stream);
     if (rc != IMBA_OK) return rc;
-    IMBA_CUDA(imba_sort_hits_by_material(it->part, it->hits, S.indices, S.material_count, (int*)it->shadow_states, slots, it->count[cur], 0, capacity, it->stream, false), IMBA_ERR_CUDA);
+    // IMBA_VCM_SORT=1: the reference's order of work (compact_hits + sort_by_material, vcm.cpp:197-210, 327-340); default: queue order
+    const bool sort = getenv("IMBA_VCM_SORT") != nullptr;
+    if (sort) IMBA_CUDA(imba_sort_hits_by_material(it->part, it->hits, S.indices, S.material_count, (int*)it->shadow_states, slots, it->count[cur], 0, capacity, it->stream, false), IMBA_ERR_CUDA);
     IMBA_CUDA(cudaMemsetAsync(it->count[cur ^ 1], 0, sizeof(int), it->stream), IMBA_ERR_CUDA);
-    const VcmLaunch a = base_launch(it, cur, capacity);
+    const VcmLaunch a = base_launch(it, cur, capacity, sort);
     IMBA_CUDA(light ? imba_vcm_light_shade(algo, a, it->stream) : imba_vcm_camera_shade(algo, a, it->stream), IMBA_ERR_CUDA);
     const bool shadows = light ? algo != IMBA_ALGO_PPM : algo != IMBA_ALGO_PPM; // PPM emits no shadow rays in either pass
     if (shadows) {

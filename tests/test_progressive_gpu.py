@@ -95,3 +95,32 @@ def test_queue_order_shading_equals_material_sorted_shading(envmap, monkeypatch)
     assert ca == cb and ca[0] > 128 * 96 * 6
     assert a.sum() > 0 and abs(a.sum() - b.sum()) <= 2e-4 * a.sum()
     assert np.abs(a - b).max() <= 1e-3 * max(1.0, a.max())
+
+
+@pytest.mark.parametrize("algo", ["lt", "ppm", "bpt"])
+def test_vcm_family_queue_order_equals_sorted_order(algo, monkeypatch):
+    """Same switch for the bidirectional family (IMBA_VCM_SORT=1 = the reference's compact_hits + sort_by_material before both
+    shading passes).  LT and PPM: identical ray counts and images; BPT picks cache entries by index, whose order is not
+    reproducible (see the tail test), so only the light-pass count is exact there."""
+    from imbatracer_b200 import api
+    flat = load_scene("cornell_specular_front", "gpu")
+    sc = api.Scene(flat)
+    out = []
+    for sort in (False, True):
+        if sort:
+            monkeypatch.setenv("IMBA_VCM_SORT", "1")
+        else:
+            monkeypatch.delenv("IMBA_VCM_SORT", raising=False)
+        it = api.Integrator(sc, api.render_settings(flat, algo, 128, 96, seed=9))
+        it.preprocess(); it.render(4)
+        out.append((it.download(), it.ray_counts()))
+        it.close()
+    sc.close()
+    (a, ca), (b, cb) = out
+    if algo == "bpt":
+        assert ca[0] == cb[0] and abs(ca[1] - cb[1]) <= 2e-3 * ca[1]
+        assert abs(a.sum() - b.sum()) <= 0.03 * a.sum()
+        return
+    assert ca == cb
+    assert a.sum() > 0 and abs(a.sum() - b.sum()) <= 2e-4 * a.sum()
+    assert np.abs(a - b).max() <= 1e-3 * max(1.0, a.max())
