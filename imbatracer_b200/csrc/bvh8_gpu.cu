@@ -265,7 +265,8 @@ int imba_scene_build_accel_device(imba_scene* s, const imba_scene_desc* d, float
     BG_CUDA(d_work.alloc(node_cap * 4)); BG_CUDA(d_ctr.alloc(16));
     BG_CUDA(cudaMemset(d_ctr.p, 0, 16));
     unsigned* ctr = d_ctr.as<unsigned>();  // [0] next Node8, [1] next Tri48, [2] error
-    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    struct Events { cudaEvent_t a = nullptr, b = nullptr; Events() { cudaEventCreate(&a); cudaEventCreate(&b); } ~Events() { cudaEventDestroy(a); cudaEventDestroy(b); } } ev;
+    const cudaEvent_t e0 = ev.a, e1 = ev.b;
     float device_ms = 0.0f; int mesh_depth = 0;
     std::vector<int> mesh_key(d->mesh_count); std::vector<float> mesh_box(6 * (size_t)d->mesh_count);
     std::map<int, uint32_t> mesh_roots;
@@ -308,7 +309,6 @@ int imba_scene_build_accel_device(imba_scene* s, const imba_scene_desc* d, float
         memcpy(&mesh_box[6 * mi], root.v, 24);
         mesh_key[mi] = mi; mesh_roots[mi] = root_idx;
     }
-    cudaEventDestroy(e0); cudaEventDestroy(e1);
     unsigned tri_count = 0; BG_CUDA(cudaMemcpy(&tri_count, ctr + 1, 4, cudaMemcpyDeviceToHost));
     // ---- top level on the host: BVH2 over the instance boxes, converted with node indices continuing after the meshes ----
     imba_accel top;
