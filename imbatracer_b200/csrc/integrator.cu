@@ -46,6 +46,9 @@ extern "C" void imba_integrator_destroy(imba_integrator* it) {
     if (it->owns_fb) cudaFree(it->fb);
     cudaFree(it->d_stats); cudaFree(it->d_probe);
     imba_vcm_free(it);
+    if (it->shadow_stream) cudaStreamDestroy(it->shadow_stream);
+    if (it->ev_shaded) cudaEventDestroy(it->ev_shaded);
+    if (it->ev_shadow_done) cudaEventDestroy(it->ev_shadow_done);
     if (it->stream) cudaStreamDestroy(it->stream);
     delete it;
 }
@@ -68,6 +71,9 @@ extern "C" imba_integrator* imba_integrator_create(imba_scene* scene, const imba
     if (cap * it->shadow_slots > (1ll << 30)) { imba_set_error("queue capacity too large"); delete it; return nullptr; }
     it->capacity = (int)cap;
     bool ok = cudaStreamCreateWithFlags(&it->stream, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaStreamCreateWithFlags(&it->shadow_stream, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&it->ev_shaded, cudaEventDisableTiming) == cudaSuccess && cudaEventCreateWithFlags(&it->ev_shadow_done, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventRecord(it->ev_shadow_done, it->shadow_stream) == cudaSuccess;
     for (int i = 0; i < 2 && ok; ++i) {
         ok = ok && cudaMalloc((void**)&it->rays[i], (size_t)cap * 32) == cudaSuccess;
         ok = ok && cudaMalloc((void**)&it->states[i], (size_t)cap * it->state_bytes) == cudaSuccess;
@@ -137,15 +143,23 @@ static int pt_wavefront(imba_integrator* it, int cur, int capacity) {
     const int* sorted = sort ? it->part.indices : nullptr;
     if (sort) IMBA_CUDA(imba_sort_hits_by_material(it->part, it->hits, S.indices, S.material_count, (int*)it->shadow_states, 1, it->count[cur], 0, capacity, it->stream, false), IMBA_ERR_CUDA);
     IMBA_CUDA(imba_pt_miss(S, it->rays[cur], it->hits, (const PTState*)it->states[cur], sorted, it->part.bin_start + S.material_count, it->count[cur], capacity, it->fb, it->stream), IMBA_ERR_CUDA);
+    // the previous wave's shadow traversal (other stream) reads the shadow buffers and that wave's queue count, which is this
+    // wave's output count: both are rewritten below
+    IMBA_CUDA(cudaStreamWaitEvent(it->stream, it->ev_shadow_done, 0), IMBA_ERR_CUDA);
     // survivors are pushed straight into the other queue by the shading kernel (fused compaction, replaces compact_rays)
     IMBA_CUDA(cudaMemsetAsync(it->count[cur ^ 1], 0, sizeof(int), it->stream), IMBA_ERR_CUDA);
     IMBA_CUDA(imba_pt_shade(S, it->rays[cur], it->hits, (PTState*)it->states[cur], sorted, it->part.bin_start + S.material_count, it->count[cur], capacity,
                             it->shadow_rays, it->shadow_states, it->fb, it->cfg.max_path_len, it->d_stats, it->rays[cur ^ 1], (PTState*)it->states[cur ^ 1],
                             it->count[cur ^ 1], it->stream), IMBA_ERR_CUDA);
+    // shadow rays + resolve on the second stream: the next wave's closest-hit traversal does not depend on them, and the two
+    // persistent kernels fill each other's tails (small late wavefronts leave most SMs idle otherwise)
+    IMBA_CUDA(cudaEventRecord(it->ev_shaded, it->stream), IMBA_ERR_CUDA);
+    IMBA_CUDA(cudaStreamWaitEvent(it->shadow_stream, it->ev_shaded, 0), IMBA_ERR_CUDA);
     TraceRequest sq; sq.d_rays = (const imba_ray*)it->shadow_rays; sq.capacity = capacity; sq.d_count = it->count[cur]; sq.mode = 2;
     sq.d_shadow_states = it->shadow_states; sq.d_framebuffer = it->fb;
-    rc = imba_scene_trace_ex(it->scene, sq, it->stream);
+    rc = imba_scene_trace_ex(it->scene, sq, it->shadow_stream);
     if (rc != IMBA_OK) return rc;
+    IMBA_CUDA(cudaEventRecord(it->ev_shadow_done, it->shadow_stream), IMBA_ERR_CUDA);
     g_imba_launches.fetch_add((sort ? 3 : 0) + 1 + 2 + (S.env_tex >= 0 ? 1 : 0));
     return IMBA_OK;
 }
@@ -167,6 +181,8 @@ extern "C" int imba_integrator_render(imba_integrator* it, int iterations) {
             const int rc = pt_wavefront(it, cur, it->capacity);
             if (rc != IMBA_OK) return rc;
         }
+        // whoever consumes the framebuffer next does so on it->stream: order the last shadow traversal before it
+        IMBA_CUDA(cudaStreamWaitEvent(it->stream, it->ev_shadow_done, 0), IMBA_ERR_CUDA);
     }
     return IMBA_OK;
 }

@@ -52,6 +52,8 @@ struct imba_integrator {
     imba_render_settings cfg;
     DevCamera cam;
     cudaStream_t stream = nullptr;
+    // PT: the shadow + resolve traversal of wave k runs on a second stream beside the closest-hit traversal of wave k + 1
+    cudaStream_t shadow_stream = nullptr; cudaEvent_t ev_shaded = nullptr, ev_shadow_done = nullptr;
     int capacity = 0;
     int state_bytes = sizeof(PTState);
     float4* rays[2] = { nullptr, nullptr };
