@@ -42,7 +42,7 @@ static VcmLaunch base_launch(imba_integrator* it, int cur, int capacity, bool so
 }
 
 /* One wavefront of the light pass (light != 0) or of the camera pass. */
-static int vcm_wavefront(imba_integrator* it, int algo, bool light, int cur, int capacity) {
+static int vcm_wavefront(imba_integrator* it, int algo, bool light, int cur, int capacity, bool overlap_shadows = false) {
     const DeviceShading& S = *imba_shading_view(it->scene);
     const int slots = light ? 1 : it->shadow_slots;
     TraceRequest rq; rq.d_rays = (const imba_ray*)it->rays[cur]; rq.d_hits = (imba_hit*)it->hits; rq.capacity = capacity; rq.d_count = it->count[cur]; rq.mode = 0;
@@ -52,6 +52,8 @@ static int vcm_wavefront(imba_integrator* it, int algo, bool light, int cur, int
     // IMBA_VCM_SORT=1: the reference's order of work (compact_hits + sort_by_material, vcm.cpp:197-210, 327-340); default: queue order
     const bool sort = getenv("IMBA_VCM_SORT") != nullptr;
     if (sort) IMBA_CUDA(imba_sort_hits_by_material(it->part, it->hits, S.indices, S.material_count, (int*)it->shadow_states, slots, it->count[cur], 0, capacity, it->stream, false), IMBA_ERR_CUDA);
+    // (camera pass) the previous wave's shadow traversal on the second stream still reads the shadow buffers and its queue count
+    if (overlap_shadows) IMBA_CUDA(cudaStreamWaitEvent(it->stream, it->ev_shadow_done, 0), IMBA_ERR_CUDA);
     IMBA_CUDA(cudaMemsetAsync(it->count[cur ^ 1], 0, sizeof(int), it->stream), IMBA_ERR_CUDA);
     const VcmLaunch a = base_launch(it, cur, capacity, sort);
     IMBA_CUDA(light ? imba_vcm_light_shade(algo, a, it->stream) : imba_vcm_camera_shade(algo, a, it->stream), IMBA_ERR_CUDA);
@@ -60,8 +62,13 @@ static int vcm_wavefront(imba_integrator* it, int algo, bool light, int cur, int
         TraceRequest sq; sq.d_rays = (const imba_ray*)it->shadow_rays; sq.capacity = capacity * slots; sq.d_count = it->count[cur]; sq.count_mul = slots; sq.mode = 2;
         sq.d_shadow_states = it->shadow_states; sq.d_framebuffer = it->fb;
         if (it->tail_counter_next >= 0) sq.d_work_counter = it->tail_counters + it->tail_counter_next++;
-        rc = imba_scene_trace_ex(it->scene, sq, it->stream);
+        if (overlap_shadows) { // as in the PT integrator: beside the next wave's closest-hit traversal
+            IMBA_CUDA(cudaEventRecord(it->ev_shaded, it->stream), IMBA_ERR_CUDA);
+            IMBA_CUDA(cudaStreamWaitEvent(it->shadow_stream, it->ev_shaded, 0), IMBA_ERR_CUDA);
+        }
+        rc = imba_scene_trace_ex(it->scene, sq, overlap_shadows ? it->shadow_stream : it->stream);
         if (rc != IMBA_OK) return rc;
+        if (overlap_shadows) IMBA_CUDA(cudaEventRecord(it->ev_shadow_done, it->shadow_stream), IMBA_ERR_CUDA);
     }
     // survivors were pushed into the other queue by the shading kernel (fused, unordered compaction)
     g_imba_launches.fetch_add(3 + 1 + 1 + (shadows ? 1 : 0));
@@ -233,9 +240,10 @@ int imba_vcm_render_iteration(imba_integrator* it) {
         g_imba_launches.fetch_add(1);
         int cur = 0;
         for (int wave = 0; wave < it->cfg.max_path_len; ++wave, cur ^= 1) {
-            rc = vcm_wavefront(it, algo, false, cur, it->pixel_capacity);
+            rc = vcm_wavefront(it, algo, false, cur, it->pixel_capacity, true);
             if (rc != IMBA_OK) return rc;
         }
+        IMBA_CUDA(cudaStreamWaitEvent(it->stream, it->ev_shadow_done, 0), IMBA_ERR_CUDA); // framebuffer consumers follow on it->stream
     }
     return IMBA_OK;
 }
