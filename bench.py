@@ -245,13 +245,13 @@ def workload_config(flat, n):
             "parallelism": "independent ray queues per GPU, no collective"}
 
 
-def run_pt(scene, flat, rank, world, barrier, dist, iters, width=1920, height=1080):
+def run_pt(scene, flat, rank, world, barrier, dist, iters, width=1920, height=1080, spp=1):
     import torch
     from imbatracer_b200 import api
-    integ = api.Integrator(scene, api.render_settings(flat, "pt", width, height, spp=1, max_path_len=10, seed=0x1234ABCD, rank=rank, rank_count=world))
+    integ = api.Integrator(scene, api.render_settings(flat, "pt", width, height, spp=spp, max_path_len=10, seed=0x1234ABCD, rank=rank, rank_count=world))
     from imbatracer_b200.distributed import ProgressiveRenderer
     integ.preprocess()
-    loop = ProgressiveRenderer(integ, width, height)   # integ.render(1) + NCCL sum of the framebuffer per iteration (overlapped with the next one)
+    loop = ProgressiveRenderer(integ, width, height, spp)   # integ.render(1) + NCCL sum of the framebuffer per iteration (overlapped with the next one)
     stream = loop.stream
     loop.step(2)
     loop.finish(); integ.sync(); barrier()
@@ -268,10 +268,10 @@ def run_pt(scene, flat, rank, world, barrier, dist, iters, width=1920, height=10
     ms = float(t[0])
     total = loop.total
     prim, shad = integ.ray_counts()
-    mean = float(total.mean()) / ((iters + 2) * world)
+    mean = float(total.mean()) / ((iters + 2) * world * spp)
     integ.close()
-    samples = width * height * iters * world
-    return {"workload": f"PT {width}x{height}, 1 spp per iteration per GPU, max path length 10, {SCENE}", "iterations": iters,
+    samples = width * height * spp * iters * world
+    return {"workload": f"PT {width}x{height}, {spp} spp per iteration per GPU (the reference's --spp), max path length 10, {SCENE}", "iterations": iters,
             "samples_per_s": samples / (ms * 1e-3), "ms_per_iteration": ms / iters, "mrays_s_per_gpu": (prim + shad) / (iters + 2) * iters / (ms * 1e-3) / 1e6,
             "framebuffer_allreduce_bytes": width * height * 12 if dist is not None else 0, "mean_radiance": mean}
 
@@ -443,6 +443,8 @@ def run_ours(args):
     e2e_s = time.perf_counter() - t0
     # configs[2]: PT 1920x1080 progressive, samples sharded over ranks, one NCCL sum of the float framebuffer per iteration
     pt = run_pt(scene, flat, rank, world, barrier, dist if world > 1 else None, iters=max(4, min(args.steps * 2, 32)))
+    # the same with 4 samples per pixel per wavefront pass: larger wavefronts amortise the tails of the late, small waves
+    pt_spp4 = run_pt(scene, flat, rank, world, barrier, dist if world > 1 else None, iters=max(2, min(args.steps, 8)), spp=4)
     sampler.stop_flag = True; sampler.join(timeout=2)
 
     t = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
@@ -477,7 +479,7 @@ def run_ours(args):
                         "steps": e2e_steps, "note": "imba_trace_host on pinned host queues, wall clock with device sync"},
                 "gpu_launches": int(launches),
                 "clocks": sampler.summary(),
-                "pt": pt, "cfg0": ours_cfg0(), "integrators": run_integrators(scene, flat), "scenes": run_extra_scenes(rank), "device_build": device_build,
+                "pt": pt, "pt_spp4": pt_spp4, "cfg0": ours_cfg0(), "integrators": run_integrators(scene, flat), "scenes": run_extra_scenes(rank), "device_build": device_build,
                 "per_kernel": {name: {"ms": per_kernel_ms[i], "mrays_s": n / per_kernel_ms[i] / 1e3} for i, (name, _) in enumerate(BATCH_ORDER)},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(),
                              "kernel": "trace_kernel<closest> on the incoherent batch", "peak_source": peak_src,
