@@ -245,15 +245,16 @@ def workload_config(flat, n):
             "parallelism": "independent ray queues per GPU, no collective"}
 
 
-def run_pt(scene, flat, rank, world, barrier, dist, iters, width=1920, height=1080, spp=1):
+def run_pt(scene, flat, rank, world, barrier, dist, iters, width=1920, height=1080, spp=1, per_pass=1):
     import torch
     from imbatracer_b200 import api
-    integ = api.Integrator(scene, api.render_settings(flat, "pt", width, height, spp=spp, max_path_len=10, seed=0x1234ABCD, rank=rank, rank_count=world))
+    integ = api.Integrator(scene, api.render_settings(flat, "pt", width, height, spp=spp, max_path_len=10, seed=0x1234ABCD, rank=rank, rank_count=world, iterations_per_pass=per_pass))
     from imbatracer_b200.distributed import ProgressiveRenderer
     integ.preprocess()
-    loop = ProgressiveRenderer(integ, width, height, spp)   # integ.render(1) + NCCL sum of the framebuffer per iteration (overlapped with the next one)
+    loop = ProgressiveRenderer(integ, width, height, spp, iterations_per_step=per_pass)   # integ.render(per_pass) + NCCL sum of the framebuffer per iteration (overlapped with the next one)
     stream = loop.stream
-    loop.step(2)
+    warm = 2 * per_pass
+    loop.step(warm)
     loop.finish(); integ.sync(); barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
@@ -268,11 +269,11 @@ def run_pt(scene, flat, rank, world, barrier, dist, iters, width=1920, height=10
     ms = float(t[0])
     total = loop.total
     prim, shad = integ.ray_counts()
-    mean = float(total.mean()) / ((iters + 2) * world * spp)
+    mean = float(total.mean()) / ((iters + warm) * world * spp)
     integ.close()
     samples = width * height * spp * iters * world
     return {"workload": f"PT {width}x{height}, {spp} spp per iteration per GPU (the reference's --spp), max path length 10, {SCENE}", "iterations": iters,
-            "samples_per_s": samples / (ms * 1e-3), "ms_per_iteration": ms / iters, "mrays_s_per_gpu": (prim + shad) / (iters + 2) * iters / (ms * 1e-3) / 1e6,
+            "samples_per_s": samples / (ms * 1e-3), "ms_per_iteration": ms / iters, "mrays_s_per_gpu": (prim + shad) / (iters + warm) * iters / (ms * 1e-3) / 1e6, "iterations_per_pass": per_pass,
             "framebuffer_allreduce_bytes": width * height * 12 if dist is not None else 0, "mean_radiance": mean}
 
 
@@ -442,7 +443,10 @@ def run_ours(args):
     barrier()
     e2e_s = time.perf_counter() - t0
     # configs[2]: PT 1920x1080 progressive, samples sharded over ranks, one NCCL sum of the float framebuffer per iteration
-    pt = run_pt(scene, flat, rank, world, barrier, dist if world > 1 else None, iters=max(4, min(args.steps * 2, 32)))
+    # 4 progressive iterations per wavefront pass (imba_render_settings::iterations_per_pass) and per framebuffer sum; every path
+    # keeps the seed of its own iteration, the image is that of single passes -- which `pt_single_pass` times for comparison
+    pt = run_pt(scene, flat, rank, world, barrier, dist if world > 1 else None, iters=4 * max(1, min(args.steps // 2, 8)), per_pass=4)
+    pt_single = run_pt(scene, flat, rank, world, barrier, dist if world > 1 else None, iters=max(4, min(args.steps * 2, 32)))
     # the same with 4 samples per pixel per wavefront pass: larger wavefronts amortise the tails of the late, small waves
     pt_spp4 = run_pt(scene, flat, rank, world, barrier, dist if world > 1 else None, iters=max(2, min(args.steps, 8)), spp=4)
     sampler.stop_flag = True; sampler.join(timeout=2)
@@ -479,7 +483,7 @@ def run_ours(args):
                         "steps": e2e_steps, "note": "imba_trace_host on pinned host queues, wall clock with device sync"},
                 "gpu_launches": int(launches),
                 "clocks": sampler.summary(),
-                "pt": pt, "pt_spp4": pt_spp4, "cfg0": ours_cfg0(), "integrators": run_integrators(scene, flat), "scenes": run_extra_scenes(rank), "device_build": device_build,
+                "pt": pt, "pt_single_pass": pt_single, "pt_spp4": pt_spp4, "cfg0": ours_cfg0(), "integrators": run_integrators(scene, flat), "scenes": run_extra_scenes(rank), "device_build": device_build,
                 "per_kernel": {name: {"ms": per_kernel_ms[i], "mrays_s": n / per_kernel_ms[i] / 1e3} for i, (name, _) in enumerate(BATCH_ORDER)},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(),
                              "kernel": "trace_kernel<closest> on the incoherent batch", "peak_source": peak_src,

@@ -63,7 +63,7 @@ class RenderSettings(C.Structure):
                 ("cam_pos", C.c_float * 3), ("cam_dir", C.c_float * 3), ("cam_up", C.c_float * 3),
                 ("spp", C.c_int32), ("max_path_len", C.c_int32), ("light_path_count", C.c_int32),
                 ("num_connections", C.c_int32), ("num_knn", C.c_int32), ("radius_factor", C.c_float),
-                ("seed", C.c_uint64), ("rank", C.c_int32), ("rank_count", C.c_int32)]
+                ("seed", C.c_uint64), ("rank", C.c_int32), ("rank_count", C.c_int32), ("iterations_per_pass", C.c_int32), ("reserved", C.c_int32)]
 
 
 ALGO = {"pt": 0, "bpt": 1, "vcm": 2, "ppm": 3, "vcm_pt": 4, "lt": 5}

@@ -79,14 +79,14 @@ def hits_from_device(hits) -> np.ndarray:
 
 
 def render_settings(flat, algorithm="pt", width=512, height=512, fov=60.0, spp=1, max_path_len=10, light_path_count=0,
-                    num_connections=1, num_knn=10, radius_factor=2.0, seed=1, rank=0, rank_count=1):
+                    num_connections=1, num_knn=10, radius_factor=2.0, seed=1, rank=0, rank_count=1, iterations_per_pass=1):
     """UserSettings defaults of the reference (frontend/cmd_line.h:61-79) + the camera of the .scene file."""
     s = abi.RenderSettings()
     s.algorithm = abi.ALGO[algorithm]; s.width = width; s.height = height; s.fov = fov
     s.cam_pos[:] = [float(x) for x in flat.cam[0:3]]; s.cam_dir[:] = [float(x) for x in flat.cam[3:6]]; s.cam_up[:] = [float(x) for x in flat.cam[6:9]]
     s.spp = spp; s.max_path_len = max_path_len; s.light_path_count = light_path_count or width * height // 2
     s.num_connections = num_connections; s.num_knn = num_knn; s.radius_factor = radius_factor
-    s.seed = seed; s.rank = rank; s.rank_count = rank_count
+    s.seed = seed; s.rank = rank; s.rank_count = rank_count; s.iterations_per_pass = iterations_per_pass
     return s
 
 

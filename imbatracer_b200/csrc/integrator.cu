@@ -64,10 +64,11 @@ extern "C" imba_integrator* imba_integrator_create(imba_scene* scene, const imba
     imba_integrator* it = new imba_integrator;
     it->scene = scene; it->cfg = *s; it->cam = make_camera(*s);
     if (it->cfg.rank_count <= 0) { it->cfg.rank_count = 1; it->cfg.rank = 0; }
+    it->cfg.iterations_per_pass = vcm ? 1 : std::min(std::max(it->cfg.iterations_per_pass, 1), 16);
     it->pixel_capacity = s->width * s->height * s->spp;
     it->state_bytes = vcm ? (int)sizeof(VCMState) : (int)sizeof(PTState);
     it->shadow_slots = vcm ? s->num_connections + 1 : 1;
-    const long long cap = std::max((long long)s->width * s->height * s->spp, vcm ? (long long)s->light_path_count : 0ll);
+    const long long cap = std::max((long long)s->width * s->height * s->spp * it->cfg.iterations_per_pass, vcm ? (long long)s->light_path_count : 0ll);
     if (cap * it->shadow_slots > (1ll << 30)) { imba_set_error("queue capacity too large"); delete it; return nullptr; }
     it->capacity = (int)cap;
     bool ok = cudaStreamCreateWithFlags(&it->stream, cudaStreamNonBlocking) == cudaSuccess;
@@ -166,21 +167,29 @@ static int pt_wavefront(imba_integrator* it, int cur, int capacity) {
 
 extern "C" int imba_integrator_render(imba_integrator* it, int iterations) {
     if (!it || iterations < 0) { imba_set_error("invalid argument"); return IMBA_ERR_INVALID; }
-    for (int k = 0; k < iterations; ++k, ++it->iteration) {
+    for (int k = 0; k < iterations;) {
         if (it->cfg.algorithm != IMBA_ALGO_PT) {
             const int rc = imba_vcm_render_iteration(it);
             if (rc != IMBA_OK) return rc;
+            ++k; ++it->iteration;
             continue;
         }
-        const uint64_t global_iter = it->iteration * (uint64_t)it->cfg.rank_count + (uint64_t)it->cfg.rank;
-        const uint32_t seed_base = imba_iteration_seed(it->cfg.seed, global_iter, 0);
-        IMBA_CUDA(imba_pt_raygen(it->cam, it->cfg.spp, seed_base, 0, it->capacity, it->rays[0], (PTState*)it->states[0], it->count[0], it->stream), IMBA_ERR_CUDA);
+        // a group of consecutive iterations as one pass (iterations_per_pass); each keeps its own seed base
+        const int group = std::min(it->cfg.iterations_per_pass, iterations - k);
+        PtSeeds seeds;
+        for (int g = 0; g < group; ++g) {
+            const uint64_t global_iter = (it->iteration + g) * (uint64_t)it->cfg.rank_count + (uint64_t)it->cfg.rank;
+            seeds.base[g] = imba_iteration_seed(it->cfg.seed, global_iter, 0);
+        }
+        const int rays_in_pass = it->pixel_capacity * group;
+        IMBA_CUDA(imba_pt_raygen(it->cam, it->cfg.spp, seeds, it->pixel_capacity, 0, rays_in_pass, it->rays[0], (PTState*)it->states[0], it->count[0], it->stream), IMBA_ERR_CUDA);
         g_imba_launches.fetch_add(1);
         int cur = 0;
         for (int wave = 0; wave < it->cfg.max_path_len; ++wave, cur ^= 1) {
-            const int rc = pt_wavefront(it, cur, it->capacity);
+            const int rc = pt_wavefront(it, cur, rays_in_pass);
             if (rc != IMBA_OK) return rc;
         }
+        k += group; it->iteration += group;
         // whoever consumes the framebuffer next does so on it->stream: order the last shadow traversal before it
         IMBA_CUDA(cudaStreamWaitEvent(it->stream, it->ev_shadow_done, 0), IMBA_ERR_CUDA);
     }

@@ -91,7 +91,8 @@ uint32_t imba_iteration_seed(uint64_t seed, uint64_t global_iteration, uint32_t 
 
 
 
-cudaError_t imba_pt_raygen(const DevCamera& cam, int spp, uint32_t seed_base, int first, int count, float4* rays, PTState* states, int* count_out, cudaStream_t st);
+struct PtSeeds { uint32_t base[16]; };   // seed base of every progressive iteration of one pass
+cudaError_t imba_pt_raygen(const DevCamera& cam, int spp, const PtSeeds& seeds, int per_iteration, int first, int count, float4* rays, PTState* states, int* count_out, cudaStream_t st);
 cudaError_t imba_pt_shade(const DeviceShading& S, float4* rays, const int4* hits, PTState* states, const int* sorted, const int* hit_count_ptr, const int* queue_count_ptr, int capacity,
                           float4* shadow_rays, ShadowState* shadow_states, float* fb, int max_path_len, unsigned long long* ray_stats,
                           float4* out_rays, PTState* out_states, int* out_count, cudaStream_t st);

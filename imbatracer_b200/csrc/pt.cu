@@ -15,11 +15,15 @@ __device__ __forceinline__ void add_contribution(float* fb, int pixel, V3 c) {
     atomicAdd(p, c.x); atomicAdd(p + 1, c.y); atomicAdd(p + 2, c.z);
 }
 
-__global__ void pt_raygen_kernel(DevCamera cam, int spp, uint32_t seed_base, int first, int count, float4* rays, PTState* states, int* count_out) {
+__global__ void pt_raygen_kernel(DevCamera cam, int spp, PtSeeds seeds, int per_iteration, int first, int count, float4* rays, PTState* states, int* count_out) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k == 0) *count_out = count;
     if (k >= count) return;
-    const int i = first + k;
+    // several progressive iterations may share one pass (imba_render_settings::iterations_per_pass): slot k belongs to
+    // iteration k / per_iteration of the group and is seeded exactly as in a pass of its own
+    const int sub = k / per_iteration;
+    const int i = first + k - sub * per_iteration;
+    const uint32_t seed_base = seeds.base[sub];
     const int pixel_idx = i / spp, sample_idx = i % spp;
     const int y = pixel_idx / cam.width, x = pixel_idx % cam.width;
     Rng rng; rng.s = seed_primary(seed_base, i, pixel_idx);
@@ -177,8 +181,8 @@ __global__ void clear_shadow_kernel(ShadowState* s, int n) {
 
 } // namespace
 
-cudaError_t imba_pt_raygen(const DevCamera& cam, int spp, uint32_t seed_base, int first, int count, float4* rays, PTState* states, int* count_out, cudaStream_t st) {
-    pt_raygen_kernel<<<(std::max(count, 1) + 255) / 256, 256, 0, st>>>(cam, spp, seed_base, first, count, rays, states, count_out);
+cudaError_t imba_pt_raygen(const DevCamera& cam, int spp, const PtSeeds& seeds, int per_iteration, int first, int count, float4* rays, PTState* states, int* count_out, cudaStream_t st) {
+    pt_raygen_kernel<<<(std::max(count, 1) + 255) / 256, 256, 0, st>>>(cam, spp, seeds, per_iteration, first, count, rays, states, count_out);
     return cudaGetLastError();
 }
 

@@ -38,8 +38,10 @@ class ProgressiveRenderer:
     and the NCCL sum + accumulation of iteration k runs on a second stream while iteration k+1 is being rendered (events order
     the hand-over both ways), so the collective costs no device time as long as it is shorter than one iteration."""
 
-    def __init__(self, integrator, width, height, spp=1, group=None, overlap=None):
-        self.integ, self.group, self.spp = integrator, group, spp
+    def __init__(self, integrator, width, height, spp=1, group=None, overlap=None, iterations_per_step=1):
+        """iterations_per_step: progressive iterations rendered (and summed over the ranks) together; pair it with the
+        integrator's `iterations_per_pass` so that PT renders them as one large wavefront pass."""
+        self.integ, self.group, self.spp, self.per_step = integrator, group, spp, max(1, int(iterations_per_step))
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.overlap = (self.world > 1) if overlap is None else bool(overlap)
         self.fbs = [torch.zeros(width * height * 3, dtype=torch.float32, device="cuda") for _ in range(2 if self.overlap else 1)]
@@ -53,24 +55,26 @@ class ProgressiveRenderer:
             self.consumed = [torch.cuda.Event() for _ in range(2)]
             for e in self.consumed:
                 e.record(self.comm)
-        self.iterations = 0
+        self.iterations = 0; self.steps = 0
         self.shape = (height, width, 3)
 
     def step(self, iterations=1):
-        for _ in range(iterations):
+        done = 0
+        while done < iterations:
+            n = min(self.per_step, iterations - done)
             if not self.overlap:
-                self.integ.render(1)
+                self.integ.render(n)
                 accumulate_iteration(self.fb, self.total, self.group, self.stream)
             else:
-                k = self.iterations % 2
-                self.stream.wait_event(self.consumed[k])          # buffer k was summed and cleared two iterations ago
+                k = self.steps % 2
+                self.stream.wait_event(self.consumed[k])          # buffer k was summed and cleared two steps ago
                 self.integ.set_framebuffer(self.fbs[k])
-                self.integ.render(1)
+                self.integ.render(n)
                 self.rendered[k].record(self.stream)
                 self.comm.wait_event(self.rendered[k])
                 accumulate_iteration(self.fbs[k], self.total, self.group, self.comm)
                 self.consumed[k].record(self.comm)
-            self.iterations += 1
+            self.iterations += n; self.steps += 1; done += n
 
     def finish(self):
         """Orders everything outstanding on the reduction stream before later work on the integrator's stream."""

@@ -124,3 +124,22 @@ def test_vcm_family_queue_order_equals_sorted_order(algo, monkeypatch):
     assert ca == cb
     assert a.sum() > 0 and abs(a.sum() - b.sum()) <= 2e-4 * a.sum()
     assert np.abs(a - b).max() <= 1e-3 * max(1.0, a.max())
+
+
+def test_iterations_per_pass_gives_the_image_of_single_passes():
+    """imba_render_settings::iterations_per_pass: several progressive iterations as one large wavefront pass; every path is
+    seeded as in a pass of its own, so ray counts are identical and the images equal up to the order of the atomic adds."""
+    from imbatracer_b200 import api
+    flat = load_scene("cornell_specular_front", "gpu")
+    sc = api.Scene(flat)
+    out = []
+    for per_pass in (1, 4, 3):
+        it = api.Integrator(sc, api.render_settings(flat, "pt", 128, 96, seed=4, iterations_per_pass=per_pass))
+        it.preprocess(); it.render(8)           # 3 does not divide 8: the last group is smaller
+        out.append((it.download(), it.ray_counts()))
+        it.close()
+    sc.close()
+    for img, counts in out[1:]:
+        assert counts == out[0][1]
+        assert abs(img.sum() - out[0][0].sum()) <= 2e-4 * out[0][0].sum()
+        assert np.abs(img - out[0][0]).max() <= 1e-3 * max(1.0, out[0][0].max())
