@@ -201,8 +201,9 @@ def ours_cfg0():
     from imbatracer_b200.scene import FlatScene
     flat = FlatScene.load(os.path.join(ROOT, "tests", "golden", "scene_stilllife_proxy_gpu.npz"), "stilllife_proxy")
     sc = api.Scene(flat)
-    it = api.Integrator(sc, api.render_settings(flat, "pt", CFG0["width"], CFG0["height"], spp=1, max_path_len=CFG0["max_path_len"], seed=7))
-    it.preprocess(); it.render(2); it.sync(); it.clear()
+    it = api.Integrator(sc, api.render_settings(flat, "pt", CFG0["width"], CFG0["height"], spp=1, max_path_len=CFG0["max_path_len"], seed=7,
+                                                 iterations_per_pass=CFG0["spp"]))   # the 16 iterations as one wavefront pass of 4 Mi paths
+    it.preprocess(); it.render(CFG0["spp"]); it.sync(); it.clear()
     t0 = time.perf_counter(); it.render(CFG0["spp"]); it.sync(); dt = time.perf_counter() - t0
     img = it.download()
     prim, shad = it.ray_counts()
