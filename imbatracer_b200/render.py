@@ -3,7 +3,7 @@ final report line (frontend/render_window.cpp:84-88), so that test/run_bench.py-
 
   python -m imbatracer_b200.render scene.npz [out.png] -a pt|bpt|vcm|ppm|lt|vcm_pt -w 512 -h 512 -s SAMPLES | -t SECONDS
          [--spp N] [--max-path-len N] [--light-path-count N] [-r RADIUS_FACTOR] [-c CONNECTIONS] [-k KNN] [--gamma G]
-         [--compare ref.png]
+         [--compare ref.png] [--iterations-per-pass N]
 
 `scene.npz` is a flattened scene (imbatracer_b200/scene.py), i.e. what the reference's loader + BVH builders produce and a
 host program hands to imba_scene_create; loading OBJ/MTL files is the reference's job (out of scope).
@@ -53,6 +53,7 @@ def main(argv=None):
     ap.add_argument("-c", type=int, default=1); ap.add_argument("-k", type=int, default=10); ap.add_argument("--gamma", type=float, default=0.5)
     ap.add_argument("--seed", type=int, default=1); ap.add_argument("--compare"); ap.add_argument("--help", action="help")
     ap.add_argument("--intermediate-path"); ap.add_argument("--intermediate-time", type=float, default=10.0)
+    ap.add_argument("--iterations-per-pass", type=int, default=1, help="PT: progressive iterations rendered as one wavefront pass (same image)")
     a = ap.parse_args(argv)
     if a.s <= 0 and a.t <= 0:
         a.s = 16
@@ -69,14 +70,15 @@ def main(argv=None):
     flat = FlatScene.load(a.scene)
     scene = api.Scene(flat)
     st = api.render_settings(flat, a.algo, a.w, a.h, fov=a.f, spp=a.spp, max_path_len=a.max_path_len, light_path_count=a.light_path_count,
-                             num_connections=a.c, num_knn=a.k, radius_factor=a.r, seed=a.seed, rank=rank, rank_count=world)
+                             num_connections=a.c, num_knn=a.k, radius_factor=a.r, seed=a.seed, rank=rank, rank_count=world,
+                             iterations_per_pass=a.iterations_per_pass)
     integ = api.Integrator(scene, st)
     integ.preprocess()
-    loop = ProgressiveRenderer(integ, a.w, a.h, a.spp)
+    loop = ProgressiveRenderer(integ, a.w, a.h, a.spp, iterations_per_step=a.iterations_per_pass if a.algo == "pt" else 1)
     t0 = time.time()
     next_dump = a.intermediate_time
     while True:
-        loop.step(1)
+        loop.step(loop.per_step)
         samples = loop.iterations * world * a.spp
         if a.s > 0 and samples >= a.s:
             break
