@@ -89,9 +89,9 @@ extern "C" void imba_scene_destroy(imba_scene* s) {
     if (!s) return;
     cudaFree(s->d_nodes); cudaFree(s->d_tris); cudaFree(s->d_insts); cudaFree(s->d_counters);
     if (s->owns_masks) { cudaFree(s->d_mask_indices); cudaFree(s->d_mask_texcoords); cudaFree(s->d_masks); cudaFree(s->d_mask_buffer); }
-    for (int i = 0; i < imba_scene::kStageSlots; ++i) {
-        cudaFree(s->d_stage_rays[i]); cudaFree(s->d_stage_hits[i]);
-        if (s->stage_stream[i]) cudaStreamDestroy(s->stage_stream[i]);
+    for (auto& set : s->stage) for (int i = 0; i < imba_scene::kStageSlots; ++i) {
+        cudaFree(set.d_rays[i]); cudaFree(set.d_hits[i]);
+        if (set.stream[i]) cudaStreamDestroy(set.stream[i]);
     }
     imba_shading_free(s);
     delete s;
@@ -153,31 +153,38 @@ extern "C" int imba_trace(imba_scene* s, const imba_ray* d_rays, imba_hit* d_hit
     return imba_scene_trace(s, d_rays, d_hits, count, any_hit, d_counters, (cudaStream_t)stream);
 }
 
-static std::mutex g_stage_mutex;
-
-/* RayQueue::traverse_gpu / traverse_occluded_gpu (ray_queue.h:269-293, 319-343) with the copies overlapped:
- * chunks rotate over kStageSlots streams, so uploads, traversal and downloads of different chunks overlap (both copy engines busy). */
+/* RayQueue::traverse_gpu / traverse_cpu (ray_queue.h:247-343): rays and hits live in host memory.  A call takes one of the
+ * scene's staging sets (concurrent callers get different ones and overlap; a fifth caller waits) and streams its chunks
+ * through it. */
 extern "C" int imba_trace_host(imba_scene* s, const imba_ray* h_rays, imba_hit* h_hits, int count, int any_hit) {
     if (!s || count < 0 || (count > 0 && (!h_rays || !h_hits))) { imba_set_error("invalid traversal arguments"); return IMBA_ERR_INVALID; }
     if (count == 0) return IMBA_OK;
-    std::lock_guard<std::mutex> lock(g_stage_mutex);
+    IMBA_CUDA(cudaSetDevice(s->device), IMBA_ERR_CUDA);   // callers may be worker threads that never selected a device
+    imba_scene::StageSet* set = nullptr;
+    {
+        std::unique_lock<std::mutex> lock(s->stage_mutex);
+        s->stage_free.wait(lock, [&] { for (auto& c : s->stage) if (!c.busy) return true; return false; });
+        for (auto& c : s->stage) if (!c.busy) { set = &c; break; }
+        set->busy = true;
+    }
+    struct Release { imba_scene* s; imba_scene::StageSet* set; ~Release() { { std::lock_guard<std::mutex> l(s->stage_mutex); set->busy = false; } s->stage_free.notify_one(); } } release{ s, set };
     const int chunk = imba_scene::kChunkRays;
     for (int i = 0; i < imba_scene::kStageSlots; ++i) {
-        if (s->d_stage_rays[i]) continue;
-        IMBA_CUDA(cudaMalloc((void**)&s->d_stage_rays[i], (size_t)chunk * sizeof(imba_ray)), IMBA_ERR_CUDA);
-        IMBA_CUDA(cudaMalloc((void**)&s->d_stage_hits[i], (size_t)chunk * sizeof(imba_hit)), IMBA_ERR_CUDA);
-        IMBA_CUDA(cudaStreamCreateWithFlags(&s->stage_stream[i], cudaStreamNonBlocking), IMBA_ERR_CUDA);
+        if (set->d_rays[i]) continue;
+        IMBA_CUDA(cudaMalloc((void**)&set->d_rays[i], (size_t)chunk * sizeof(imba_ray)), IMBA_ERR_CUDA);
+        IMBA_CUDA(cudaMalloc((void**)&set->d_hits[i], (size_t)chunk * sizeof(imba_hit)), IMBA_ERR_CUDA);
+        IMBA_CUDA(cudaStreamCreateWithFlags(&set->stream[i], cudaStreamNonBlocking), IMBA_ERR_CUDA);
     }
     int k = 0;
     for (int first = 0; first < count; first += chunk, k = (k + 1) % imba_scene::kStageSlots) {
         const int n = count - first < chunk ? count - first : chunk;
-        cudaStream_t st = s->stage_stream[k];
-        IMBA_CUDA(cudaMemcpyAsync(s->d_stage_rays[k], h_rays + first, (size_t)n * sizeof(imba_ray), cudaMemcpyHostToDevice, st), IMBA_ERR_CUDA);
-        const int rc = imba_scene_trace(s, (const imba_ray*)s->d_stage_rays[k], (imba_hit*)s->d_stage_hits[k], n, any_hit, nullptr, st);
+        cudaStream_t st = set->stream[k];
+        IMBA_CUDA(cudaMemcpyAsync(set->d_rays[k], h_rays + first, (size_t)n * sizeof(imba_ray), cudaMemcpyHostToDevice, st), IMBA_ERR_CUDA);
+        const int rc = imba_scene_trace(s, (const imba_ray*)set->d_rays[k], (imba_hit*)set->d_hits[k], n, any_hit, nullptr, st);
         if (rc != IMBA_OK) return rc;
-        IMBA_CUDA(cudaMemcpyAsync(h_hits + first, s->d_stage_hits[k], (size_t)n * sizeof(imba_hit), cudaMemcpyDeviceToHost, st), IMBA_ERR_CUDA);
+        IMBA_CUDA(cudaMemcpyAsync(h_hits + first, set->d_hits[k], (size_t)n * sizeof(imba_hit), cudaMemcpyDeviceToHost, st), IMBA_ERR_CUDA);
     }
-    for (int i = 0; i < imba_scene::kStageSlots; ++i) IMBA_CUDA(cudaStreamSynchronize(s->stage_stream[i]), IMBA_ERR_CUDA);
+    for (int i = 0; i < imba_scene::kStageSlots; ++i) IMBA_CUDA(cudaStreamSynchronize(set->stream[i]), IMBA_ERR_CUDA);
     return IMBA_OK;
 }
 

@@ -2,7 +2,9 @@
 #ifndef IMBA_API_COMMON_H
 #define IMBA_API_COMMON_H
 #include <atomic>
+#include <condition_variable>
 #include <cstdarg>
+#include <mutex>
 #include <cstdio>
 #include <string>
 #include <vector>
@@ -35,11 +37,15 @@ struct imba_scene {
     // work counters (one per in-flight launch)
     unsigned* d_counters = nullptr; std::atomic<unsigned> next_counter{ 0 };
     static constexpr unsigned kCounters = 4096;
-    // staging for host-buffer traversal
+    // staging for host-buffer traversal: kStageSets independent pipelines (one per concurrent caller: the reference's
+    // TileScheduler threads call traverse concurrently on disjoint queues, tile_scheduler.h:69-78), each rotating its chunks over
+    // kStageSlots streams so that H2D, traversal and D2H of different chunks overlap
     static constexpr int kChunkRays = 1 << 19;   // 16 MiB of rays up, 8 MiB of hits down per chunk
-    static constexpr int kStageSlots = 4;        // chunks in flight: H2D, traversal and D2H of different chunks overlap
-    float4*   d_stage_rays[kStageSlots] = {}; int4* d_stage_hits[kStageSlots] = {};
-    cudaStream_t stage_stream[kStageSlots] = {};
+    static constexpr int kStageSlots = 4;
+    static constexpr int kStageSets = 4;
+    struct StageSet { float4* d_rays[kStageSlots] = {}; int4* d_hits[kStageSlots] = {}; cudaStream_t stream[kStageSlots] = {}; bool busy = false; };
+    StageSet stage[kStageSets];
+    std::mutex stage_mutex; std::condition_variable stage_free;
     // shading data (geometry, materials, lights, textures), null until uploaded
     DeviceShading* shading = nullptr;
     int grid_cache[12] = { 0 };

@@ -189,3 +189,27 @@ def test_l1_drop_in_entry_points(torch_cuda):
         assert got.tobytes() == want.tobytes(), layout
         assert np.array_equal(occ, want_occ), layout
     L.imba_l1_invalidate()
+
+
+@pytest.mark.gpu
+def test_concurrent_host_buffer_calls(torch_cuda):
+    """The reference's TileScheduler threads call traverse concurrently on disjoint queues with the shared scene
+    (tile_scheduler.h:69-78): imba_trace_host gives every concurrent caller its own staging pipeline; more callers than
+    pipelines wait their turn.  Every call must return exactly its own hits."""
+    from concurrent.futures import ThreadPoolExecutor
+    from imbatracer_b200 import api
+    from tests import refapi, raygen
+    flat = load_scene("cornell_water", "gpu")
+    scene = api.Scene(flat)
+    try:
+        jobs = [(np.ascontiguousarray(raygen.random_rays(flat, 300_000 + 77 * k, 100 + k)), bool(k & 1)) for k in range(7)]   # 7 callers > 4 pipelines
+        with ThreadPoolExecutor(len(jobs)) as pool:
+            got = list(pool.map(lambda j: scene.trace_host(j[0], any_hit=j[1]), jobs))
+        for (rays, any_hit), hits in zip(jobs, got):
+            want = refapi.trace_oracle(flat, rays, any_hit=any_hit)
+            if any_hit:
+                assert np.array_equal(hits["tri_id"] >= 0, want["tri_id"] >= 0)
+            else:
+                assert hits.tobytes() == want.tobytes()
+    finally:
+        scene.close()
