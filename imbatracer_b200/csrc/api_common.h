@@ -40,7 +40,10 @@ struct imba_scene {
     // staging for host-buffer traversal: kStageSets independent pipelines (one per concurrent caller: the reference's
     // TileScheduler threads call traverse concurrently on disjoint queues, tile_scheduler.h:69-78), each rotating its chunks over
     // kStageSlots streams so that H2D, traversal and D2H of different chunks overlap
-    static constexpr int kChunkRays = 1 << 19;   // 16 MiB of rays up, 8 MiB of hits down per chunk
+#ifndef IMBA_CHUNK_LOG2
+#define IMBA_CHUNK_LOG2 19
+#endif
+    static constexpr int kChunkRays = 1 << IMBA_CHUNK_LOG2;   // 2^19: 16 MiB of rays up, 8 MiB of hits down per chunk
     static constexpr int kStageSlots = 4;
     static constexpr int kStageSets = 4;
     struct StageSet { float4* d_rays[kStageSlots] = {}; int4* d_hits[kStageSlots] = {}; cudaStream_t stream[kStageSlots] = {}; bool busy = false; };
