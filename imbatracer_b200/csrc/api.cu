@@ -5,6 +5,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <sched.h>
 
 std::atomic<uint64_t> g_imba_launches{ 0 };
 static thread_local std::string t_error;
@@ -92,6 +93,7 @@ extern "C" void imba_scene_destroy(imba_scene* s) {
     for (auto& set : s->stage) for (int i = 0; i < imba_scene::kStageSlots; ++i) {
         cudaFree(set.d_rays[i]); cudaFree(set.d_hits[i]);
         if (set.stream[i]) cudaStreamDestroy(set.stream[i]);
+        if (set.done[i]) cudaEventDestroy(set.done[i]);
     }
     imba_shading_free(s);
     delete s;
@@ -174,6 +176,7 @@ extern "C" int imba_trace_host(imba_scene* s, const imba_ray* h_rays, imba_hit* 
         IMBA_CUDA(cudaMalloc((void**)&set->d_rays[i], (size_t)chunk * sizeof(imba_ray)), IMBA_ERR_CUDA);
         IMBA_CUDA(cudaMalloc((void**)&set->d_hits[i], (size_t)chunk * sizeof(imba_hit)), IMBA_ERR_CUDA);
         IMBA_CUDA(cudaStreamCreateWithFlags(&set->stream[i], cudaStreamNonBlocking), IMBA_ERR_CUDA);
+        IMBA_CUDA(cudaEventCreateWithFlags(&set->done[i], cudaEventDisableTiming), IMBA_ERR_CUDA);
     }
     int k = 0;
     for (int first = 0; first < count; first += chunk, k = (k + 1) % imba_scene::kStageSlots) {
@@ -184,7 +187,14 @@ extern "C" int imba_trace_host(imba_scene* s, const imba_ray* h_rays, imba_hit* 
         if (rc != IMBA_OK) return rc;
         IMBA_CUDA(cudaMemcpyAsync(h_hits + first, set->d_hits[k], (size_t)n * sizeof(imba_hit), cudaMemcpyDeviceToHost, st), IMBA_ERR_CUDA);
     }
-    for (int i = 0; i < imba_scene::kStageSlots; ++i) IMBA_CUDA(cudaStreamSynchronize(set->stream[i]), IMBA_ERR_CUDA);
+    // poll and yield: as quick as spinning when cores are free, but several callers per process and several processes per host
+    // (one per GPU) do not starve each other of the cores they need to enqueue their next chunks
+    for (int i = 0; i < imba_scene::kStageSlots; ++i) IMBA_CUDA(cudaEventRecord(set->done[i], set->stream[i]), IMBA_ERR_CUDA);
+    for (int i = 0; i < imba_scene::kStageSlots; ++i) {
+        cudaError_t e;
+        while ((e = cudaEventQuery(set->done[i])) == cudaErrorNotReady) sched_yield();
+        IMBA_CUDA(e, IMBA_ERR_CUDA);
+    }
     return IMBA_OK;
 }
 

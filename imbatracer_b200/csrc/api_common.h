@@ -46,7 +46,8 @@ struct imba_scene {
     static constexpr int kChunkRays = 1 << IMBA_CHUNK_LOG2;   // 2^19: 16 MiB of rays up, 8 MiB of hits down per chunk
     static constexpr int kStageSlots = 4;
     static constexpr int kStageSets = 4;
-    struct StageSet { float4* d_rays[kStageSlots] = {}; int4* d_hits[kStageSlots] = {}; cudaStream_t stream[kStageSlots] = {}; bool busy = false; };
+    struct StageSet { float4* d_rays[kStageSlots] = {}; int4* d_hits[kStageSlots] = {}; cudaStream_t stream[kStageSlots] = {};
+                      cudaEvent_t done[kStageSlots] = {}; bool busy = false; };
     StageSet stage[kStageSets];
     std::mutex stage_mutex; std::condition_variable stage_free;
     // shading data (geometry, materials, lights, textures), null until uploaded
