@@ -40,12 +40,12 @@ uint32_t imba_iteration_seed(uint64_t seed, uint64_t global_iteration, uint32_t 
 
 extern "C" void imba_integrator_destroy(imba_integrator* it) {
     if (!it) return;
+    imba_vcm_free(it);   // also points the queue members back at the buffers allocated at creation
     for (int i = 0; i < 2; ++i) { cudaFree(it->rays[i]); cudaFree(it->states[i]); cudaFree(it->count[i]); }
     cudaFree(it->hits); cudaFree(it->shadow_rays); cudaFree(it->shadow_states);
     imba_partition_free(it->part);
     if (it->owns_fb) cudaFree(it->fb);
     cudaFree(it->d_stats); cudaFree(it->d_probe);
-    imba_vcm_free(it);
     if (it->shadow_stream) cudaStreamDestroy(it->shadow_stream);
     if (it->ev_shaded) cudaEventDestroy(it->ev_shaded);
     if (it->ev_shadow_done) cudaEventDestroy(it->ev_shadow_done);
@@ -168,12 +168,7 @@ static int pt_wavefront(imba_integrator* it, int cur, int capacity) {
 extern "C" int imba_integrator_render(imba_integrator* it, int iterations) {
     if (!it || iterations < 0) { imba_set_error("invalid argument"); return IMBA_ERR_INVALID; }
     for (int k = 0; k < iterations;) {
-        if (it->cfg.algorithm != IMBA_ALGO_PT) {
-            const int rc = imba_vcm_render_iteration(it);
-            if (rc != IMBA_OK) return rc;
-            ++k; ++it->iteration;
-            continue;
-        }
+        if (it->cfg.algorithm != IMBA_ALGO_PT) return imba_vcm_render(it, iterations);
         // a group of consecutive iterations as one pass (iterations_per_pass); each keeps its own seed base
         const int group = std::min(it->cfg.iterations_per_pass, iterations - k);
         PtSeeds seeds;

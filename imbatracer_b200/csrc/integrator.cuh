@@ -76,6 +76,18 @@ struct imba_integrator {
     float4* photon_pos = nullptr; int* merge_found = nullptr; // SoA copy of the photon positions; k-NN lists of the camera wavefront
     float   base_radius = 0.0f;
     struct VcmParams* d_params = nullptr;    // per-iteration constants in device memory
+    // Pipelining of consecutive iterations inside one render(n) call (vcm_host.cu: imba_vcm_render): the camera pass of iteration
+    // k-1 runs on the main stream beside the latency-bound tail of the light pass of iteration k (side stream).  The data a
+    // camera pass reads (vertex cache, photon grid, parameters) is therefore double-buffered, and the camera pass has queues of
+    // its own; the members above (cache, grid, d_params, rays, ...) always point at the set the next launches are to use.
+    struct VcmSet { struct DevLightVertex* cache; int* cache_last; struct GridParams* grid; int* cells; struct DevPhoton* photons; float4* photon_pos; struct VcmParams* d_params; };
+    struct QueueSet { float4* rays[2]; char* states[2]; int* count[2]; int4* hits; float4* shadow_rays; ShadowState* shadow_states; };
+    VcmSet vset[2] = {};
+    QueueSet light_q = {}, cam_q = {};
+    struct VcmParams* h_params = nullptr;    // host copies of the two parameter blocks
+    unsigned* d_table_state = nullptr;       // current size of the photon hash table (only grows, rangesearch.h:33-43), shared by both grids
+    cudaStream_t tail_stream = nullptr; cudaEvent_t ev_light_done = nullptr, ev_tail_done = nullptr;
+    bool camera_pending = false; uint64_t pending_global_iter = 0; int pending_set = 0;
     unsigned* tail_counters = nullptr; int tail_counter_next = -1; // dedicated traversal work counters of the captured graph
     cudaGraphExec_t tail_graph = nullptr;    // captured light-pass wavefronts for the long tail of small queues
     // the captured launches hold the framebuffer pointer: graphs of other framebuffers the caller alternates between are parked here
@@ -85,7 +97,7 @@ struct imba_integrator {
 int imba_vcm_allocate(imba_integrator* it);
 void imba_vcm_free(imba_integrator* it);
 int imba_vcm_preprocess(imba_integrator* it);
-int imba_vcm_render_iteration(imba_integrator* it);
+int imba_vcm_render(imba_integrator* it, int iterations);
 uint32_t imba_iteration_seed(uint64_t seed, uint64_t global_iteration, uint32_t stream_id);
 
 

@@ -297,7 +297,7 @@ __global__ void __launch_bounds__(256) grid_bbox_kernel(const DevLightVertex* ca
 }
 
 /* bbox_.max += extents * 0.001f; bbox_.min -= ... (rangesearch.h:45-47); also publishes count_ = min(size, last_) */
-__global__ void grid_prepare_kernel(const int* bbox, const int* last, int capacity, GridParams* g, float radius) {
+__global__ void grid_prepare_kernel(const int* bbox, const int* last, int capacity, GridParams* g, float radius, unsigned* table_state) {
     const int n = min(*last, capacity);
     float lo[3], hi[3];
     for (int a = 0; a < 3; ++a) { lo[a] = from_ordered(bbox[a]); hi[a] = from_ordered(bbox[3 + a]); }
@@ -307,9 +307,13 @@ __global__ void grid_prepare_kernel(const int* bbox, const int* last, int capaci
     g->radius_sqr = radius * radius; g->inv_cell_size = 1.f / (radius * 2.f); g->count = n;
     // the reference's table has 2 * photon_count cells and is only re-allocated when it must grow; the size matters for
     // results, not just speed: two of the 8 query cells that collide make their photons count twice (rangesearch.h:96-127)
+    // (the size lives in *table_state, shared by the two double-buffered grids of the pipelined loop: it must follow the history
+    // of ALL iterations, as the reference's single grid does)
     const unsigned want = (unsigned)n * 2u;
-    if (g->table < want) g->table = want;
-    if (g->table == 0) g->table = 1;
+    unsigned t = *table_state;
+    if (t < want) t = want;
+    if (t == 0) t = 1;
+    *table_state = t; g->table = t;
 }
 
 __device__ __forceinline__ unsigned cell_hash(unsigned x, unsigned y, unsigned z, unsigned table) {
@@ -740,13 +744,13 @@ cudaError_t imba_vcm_light_tail(int algo, bool masks, const VcmLaunch& a, const 
 
 /* HashGrid::build on the vertex cache; `cells` has `table` + 1 ints, block_sums (table / 2048 + 1) ints */
 cudaError_t imba_grid_build(const DevLightVertex* cache, const int* cache_last, int cache_capacity, float radius, GridParams* grid, int* bbox, int* cells, unsigned table,
-                            int* block_sums, DevPhoton* photons, float4* photon_pos, bool build_cells, cudaStream_t st) {
+                            int* block_sums, DevPhoton* photons, float4* photon_pos, bool build_cells, unsigned* table_state, cudaStream_t st) {
     static const int init_bbox[6] = { 0x7f7fffff, 0x7f7fffff, 0x7f7fffff, (int)(0xff7fffffu ^ 0x7fffffffu), (int)(0xff7fffffu ^ 0x7fffffffu), (int)(0xff7fffffu ^ 0x7fffffffu) };
     cudaError_t e = cudaMemcpyAsync(bbox, init_bbox, sizeof(init_bbox), cudaMemcpyHostToDevice, st);
     if (e != cudaSuccess) return e;
     const int blocks = (std::max(cache_capacity, 1) + 255) / 256;
     if (build_cells) grid_bbox_kernel<<<std::min(blocks, 148 * 8), 256, 0, st>>>(cache, cache_last, cache_capacity, bbox);
-    grid_prepare_kernel<<<1, 1, 0, st>>>(bbox, cache_last, cache_capacity, grid, radius);
+    grid_prepare_kernel<<<1, 1, 0, st>>>(bbox, cache_last, cache_capacity, grid, radius, table_state);
     if (build_cells) {
         if ((e = cudaMemsetAsync(cells, 0, sizeof(int) * (size_t)(table + 1), st)) != cudaSuccess) return e;
         grid_count_kernel<<<blocks, 256, 0, st>>>(cache, grid, cells, table);

@@ -34,5 +34,5 @@ cudaError_t imba_vcm_light_shade(int algo, const VcmLaunch& a, cudaStream_t st);
 cudaError_t imba_vcm_camera_shade(int algo, const VcmLaunch& a, cudaStream_t st);
 cudaError_t imba_vcm_light_tail(int algo, bool masks, const VcmLaunch& a, const TraceArgs& T, int capacity, cudaStream_t st);
 cudaError_t imba_grid_build(const DevLightVertex* cache, const int* cache_last, int cache_capacity, float radius, GridParams* grid, int* bbox, int* cells, unsigned table,
-                            int* block_sums, DevPhoton* photons, float4* photon_pos, bool build_cells, cudaStream_t st);
+                            int* block_sums, DevPhoton* photons, float4* photon_pos, bool build_cells, unsigned* table_state, cudaStream_t st);
 #endif

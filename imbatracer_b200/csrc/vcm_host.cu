@@ -75,9 +75,20 @@ static int vcm_wavefront(imba_integrator* it, int algo, bool light, int cur, int
     return IMBA_OK;
 }
 
-static int set_params(imba_integrator* it, const VcmParams& P) {
-    IMBA_CUDA(cudaMemcpyAsync(it->d_params, &P, sizeof(P), cudaMemcpyHostToDevice, it->stream), IMBA_ERR_CUDA);
-    IMBA_CUDA(cudaStreamSynchronize(it->stream), IMBA_ERR_CUDA); // P is a stack variable of the caller
+static void use_set(imba_integrator* it, int b) {
+    const imba_integrator::VcmSet& v = it->vset[b];
+    it->cache = v.cache; it->cache_last = v.cache_last; it->grid = v.grid; it->cells = v.cells; it->photons = v.photons; it->photon_pos = v.photon_pos; it->d_params = v.d_params;
+}
+static void use_queues(imba_integrator* it, const imba_integrator::QueueSet& q) {
+    for (int i = 0; i < 2; ++i) { it->rays[i] = q.rays[i]; it->states[i] = q.states[i]; it->count[i] = q.count[i]; }
+    it->hits = q.hits; it->shadow_rays = q.shadow_rays; it->shadow_states = q.shadow_states;
+}
+
+/* Parameters of the iteration into the current set's device block.  The host copy outlives the call (pageable memory: the
+ * driver has staged it when cudaMemcpyAsync returns), so no stream synchronisation is needed. */
+static int set_params(imba_integrator* it, const VcmParams& P, int b = 0) {
+    it->h_params[b] = P;
+    IMBA_CUDA(cudaMemcpyAsync(it->d_params, &it->h_params[b], sizeof(P), cudaMemcpyHostToDevice, it->stream), IMBA_ERR_CUDA);
     return IMBA_OK;
 }
 
@@ -105,7 +116,7 @@ static int build_tail_graph(imba_integrator* it, int algo) {
 }
 
 /* Traces all light paths of one iteration; returns the number of wavefronts through *waves. */
-static int light_pass(imba_integrator* it, int algo, uint32_t seed_base, int path_count, int* waves, bool use_graph) {
+static int light_pass(imba_integrator* it, int algo, uint32_t seed_base, int path_count, int* waves, bool use_graph, cudaStream_t tail_stream = nullptr) {
     const DeviceShading& S = *imba_shading_view(it->scene);
     IMBA_CUDA(cudaMemsetAsync(it->cache_last, 0, sizeof(int), it->stream), IMBA_ERR_CUDA);
     IMBA_CUDA(imba_vcm_light_raygen(S, it->d_params, seed_base, path_count, it->rays[0], (VCMState*)it->states[0], it->count[0], it->stream), IMBA_ERR_CUDA);
@@ -118,7 +129,12 @@ static int light_pass(imba_integrator* it, int algo, uint32_t seed_base, int pat
         if (use_graph && n <= mega) { // few paths left: one thread per path follows it to its end (vcm.cu: vcm_light_tail_kernel)
             TraceArgs T; imba_scene_trace_args(it->scene, &T);
             const VcmLaunch a = base_launch(it, cur, n);
-            IMBA_CUDA(imba_vcm_light_tail(algo, it->scene->has_masks, a, T, n, it->stream), IMBA_ERR_CUDA);
+            if (tail_stream) { // pipelined: the tail runs beside the previous iteration's camera pass (imba_vcm_render)
+                IMBA_CUDA(cudaEventRecord(it->ev_light_done, it->stream), IMBA_ERR_CUDA);
+                IMBA_CUDA(cudaStreamWaitEvent(tail_stream, it->ev_light_done, 0), IMBA_ERR_CUDA);
+            }
+            IMBA_CUDA(imba_vcm_light_tail(algo, it->scene->has_masks, a, T, n, tail_stream ? tail_stream : it->stream), IMBA_ERR_CUDA);
+            if (tail_stream) IMBA_CUDA(cudaEventRecord(it->ev_tail_done, tail_stream), IMBA_ERR_CUDA);
             g_imba_launches.fetch_add(2); ++w;
             break;
         }
@@ -148,27 +164,69 @@ static int light_pass(imba_integrator* it, int algo, uint32_t seed_base, int pat
 void imba_vcm_free(imba_integrator* it) {
     if (it->tail_graph) { cudaGraphExecDestroy(it->tail_graph); it->tail_graph = nullptr; }
     for (int i = 0; i < imba_integrator::kParkedGraphs; ++i) if (it->parked_graph[i]) { cudaGraphExecDestroy(it->parked_graph[i]); it->parked_graph[i] = nullptr; }
-    cudaFree(it->d_params); it->d_params = nullptr; cudaFree(it->tail_counters); it->tail_counters = nullptr;
-    cudaFree(it->cache); cudaFree(it->cache_last); cudaFree(it->grid); cudaFree(it->grid_bbox); cudaFree(it->cells); cudaFree(it->block_sums); cudaFree(it->photons);
-    cudaFree(it->photon_pos); cudaFree(it->merge_found); it->photon_pos = nullptr; it->merge_found = nullptr;
-    it->cache = nullptr; it->cache_last = nullptr; it->grid = nullptr; it->grid_bbox = nullptr; it->cells = nullptr; it->block_sums = nullptr; it->photons = nullptr;
+    cudaFree(it->tail_counters); it->tail_counters = nullptr;
+    for (auto& v : it->vset) {
+        cudaFree(v.cache); cudaFree(v.cache_last); cudaFree(v.grid); cudaFree(v.cells); cudaFree(v.photons); cudaFree(v.photon_pos); cudaFree(v.d_params);
+        v = imba_integrator::VcmSet{};
+    }
+    cudaFree(it->grid_bbox); cudaFree(it->block_sums); cudaFree(it->merge_found); cudaFree(it->d_table_state);
+    it->grid_bbox = nullptr; it->block_sums = nullptr; it->merge_found = nullptr; it->d_table_state = nullptr;
+    it->cache = nullptr; it->cache_last = nullptr; it->grid = nullptr; it->cells = nullptr; it->photons = nullptr; it->photon_pos = nullptr; it->d_params = nullptr;
+    delete[] it->h_params; it->h_params = nullptr;
+    // camera queues of the pipelined loop; the members go back to the buffers the integrator was created with
+    if (it->light_q.rays[0]) use_queues(it, it->light_q);
+    for (int i = 0; i < 2; ++i) { cudaFree(it->cam_q.rays[i]); cudaFree(it->cam_q.states[i]); cudaFree(it->cam_q.count[i]); }
+    cudaFree(it->cam_q.hits); cudaFree(it->cam_q.shadow_rays); cudaFree(it->cam_q.shadow_states);
+    it->cam_q = imba_integrator::QueueSet{};
+    if (it->tail_stream) { cudaStreamDestroy(it->tail_stream); it->tail_stream = nullptr; }
+    if (it->ev_light_done) { cudaEventDestroy(it->ev_light_done); it->ev_light_done = nullptr; }
+    if (it->ev_tail_done) { cudaEventDestroy(it->ev_tail_done); it->ev_tail_done = nullptr; }
+    it->camera_pending = false;
 }
+
+static bool pipelined_algo(int algo) { return algo == IMBA_ALGO_BPT || algo == IMBA_ALGO_VCM || algo == IMBA_ALGO_PPM; }
 
 int imba_vcm_allocate(imba_integrator* it) {
     imba_vcm_free(it);
     const int cap = std::max(it->cache_capacity, 1);
     it->table = (unsigned)cap * 2u; // inv_load_factor = 2 (rangesearch.h:26)
-    bool ok = cudaMalloc((void**)&it->cache, (size_t)cap * sizeof(DevLightVertex)) == cudaSuccess;
-    ok = ok && cudaMalloc((void**)&it->d_params, sizeof(VcmParams)) == cudaSuccess;
-    ok = ok && cudaMalloc((void**)&it->cache_last, 16) == cudaSuccess && cudaMemset(it->cache_last, 0, 16) == cudaSuccess;
-    ok = ok && cudaMalloc((void**)&it->grid, sizeof(GridParams)) == cudaSuccess && cudaMemset(it->grid, 0, sizeof(GridParams)) == cudaSuccess;
+    // the queue buffers of the integrator are the light pass's; remember them before any swap
+    for (int i = 0; i < 2; ++i) { it->light_q.rays[i] = it->rays[i]; it->light_q.states[i] = it->states[i]; it->light_q.count[i] = it->count[i]; }
+    it->light_q.hits = it->hits; it->light_q.shadow_rays = it->shadow_rays; it->light_q.shadow_states = it->shadow_states;
+    const bool two = pipelined_algo(it->cfg.algorithm) && it->cache_capacity > 0;   // second set + camera queues only where iterations are pipelined
+    bool ok = true;
+    for (int b = 0; b < (two ? 2 : 1) && ok; ++b) {
+        imba_integrator::VcmSet& v = it->vset[b];
+        ok = ok && cudaMalloc((void**)&v.cache, (size_t)cap * sizeof(DevLightVertex)) == cudaSuccess;
+        ok = ok && cudaMalloc((void**)&v.d_params, sizeof(VcmParams)) == cudaSuccess;
+        ok = ok && cudaMalloc((void**)&v.cache_last, 16) == cudaSuccess && cudaMemset(v.cache_last, 0, 16) == cudaSuccess;
+        ok = ok && cudaMalloc((void**)&v.grid, sizeof(GridParams)) == cudaSuccess && cudaMemset(v.grid, 0, sizeof(GridParams)) == cudaSuccess;
+        ok = ok && cudaMalloc((void**)&v.cells, sizeof(int) * ((size_t)it->table + 1)) == cudaSuccess;
+        ok = ok && cudaMalloc((void**)&v.photons, (size_t)cap * sizeof(DevPhoton)) == cudaSuccess;
+        ok = ok && cudaMalloc((void**)&v.photon_pos, (size_t)cap * sizeof(float4)) == cudaSuccess;
+    }
     ok = ok && cudaMalloc((void**)&it->grid_bbox, 32) == cudaSuccess;
-    ok = ok && cudaMalloc((void**)&it->cells, sizeof(int) * ((size_t)it->table + 1)) == cudaSuccess;
+    ok = ok && cudaMalloc((void**)&it->d_table_state, 16) == cudaSuccess && cudaMemset(it->d_table_state, 0, 16) == cudaSuccess;
     ok = ok && cudaMalloc((void**)&it->block_sums, sizeof(int) * ((size_t)it->table / 2048 + 2)) == cudaSuccess;
-    ok = ok && cudaMalloc((void**)&it->photons, (size_t)cap * sizeof(DevPhoton)) == cudaSuccess;
-    ok = ok && cudaMalloc((void**)&it->photon_pos, (size_t)cap * sizeof(float4)) == cudaSuccess;
     ok = ok && cudaMalloc((void**)&it->merge_found, (size_t)(IMBA_MAX_KNN + 1) * std::max(it->capacity, 1) * sizeof(int)) == cudaSuccess;
+    it->h_params = new VcmParams[2];
+    if (two) {
+        const size_t n = (size_t)std::max(it->pixel_capacity, 1);
+        for (int i = 0; i < 2 && ok; ++i) {
+            ok = ok && cudaMalloc((void**)&it->cam_q.rays[i], n * 32) == cudaSuccess;
+            ok = ok && cudaMalloc((void**)&it->cam_q.states[i], n * it->state_bytes) == cudaSuccess;
+            ok = ok && cudaMalloc((void**)&it->cam_q.count[i], 16) == cudaSuccess;
+        }
+        ok = ok && cudaMalloc((void**)&it->cam_q.hits, n * 16) == cudaSuccess;
+        ok = ok && cudaMalloc((void**)&it->cam_q.shadow_rays, n * it->shadow_slots * 32) == cudaSuccess;
+        ok = ok && cudaMalloc((void**)&it->cam_q.shadow_states, n * it->shadow_slots * 16) == cudaSuccess;
+        ok = ok && cudaStreamCreateWithFlags(&it->tail_stream, cudaStreamNonBlocking) == cudaSuccess;
+        ok = ok && cudaEventCreateWithFlags(&it->ev_light_done, cudaEventDisableTiming) == cudaSuccess;
+        ok = ok && cudaEventCreateWithFlags(&it->ev_tail_done, cudaEventDisableTiming) == cudaSuccess;
+        ok = ok && cudaEventRecord(it->ev_tail_done, it->tail_stream) == cudaSuccess;
+    }
     if (!ok) { imba_set_error("VCM allocation failed: %s", cudaGetErrorString(cudaGetLastError())); return IMBA_ERR_CUDA; }
+    use_set(it, 0);
     return IMBA_OK;
 }
 
@@ -207,43 +265,77 @@ int imba_vcm_preprocess(imba_integrator* it) {
     return imba_vcm_allocate(it);
 }
 
-int imba_vcm_render_iteration(imba_integrator* it) {
+/* Camera pass of one iteration on the current parameter / cache set and the current queues. */
+static int camera_pass(imba_integrator* it, int algo, uint64_t global_iter) {
+    IMBA_CUDA(imba_vcm_camera_raygen(it->cam, it->d_params, it->cfg.spp, imba_iteration_seed(it->cfg.seed, global_iter, 2), it->pixel_capacity, it->rays[0],
+                                     (VCMState*)it->states[0], it->count[0], it->stream), IMBA_ERR_CUDA);
+    g_imba_launches.fetch_add(1);
+    int cur = 0;
+    for (int wave = 0; wave < it->cfg.max_path_len; ++wave, cur ^= 1) {
+        const int rc = vcm_wavefront(it, algo, false, cur, it->pixel_capacity, true);
+        if (rc != IMBA_OK) return rc;
+    }
+    IMBA_CUDA(cudaStreamWaitEvent(it->stream, it->ev_shadow_done, 0), IMBA_ERR_CUDA); // framebuffer consumers follow on it->stream
+    return IMBA_OK;
+}
+
+static void grid_stats(imba_integrator* it) { // occupancy of the photon hash grid (diagnosis only)
+    GridParams g; cudaMemcpy(&g, it->grid, sizeof(g), cudaMemcpyDeviceToHost);
+    std::vector<int> ends(g.table);
+    cudaMemcpy(ends.data(), it->cells, sizeof(int) * g.table, cudaMemcpyDeviceToHost);
+    long long used = 0, sq = 0; int mx = 0, prev = 0; std::vector<int> sizes;
+    for (unsigned c = 0; c < g.table; ++c) { const int n = ends[c] - prev; prev = ends[c]; if (n > 0) { ++used; sq += (long long)n * n; mx = std::max(mx, n); sizes.push_back(n); } }
+    std::sort(sizes.begin(), sizes.end());
+    fprintf(stderr, "[imba] photon grid: %d photons, table %u, %lld cells used, largest %d, median %d, p99 %d, mean photons scanned per visited photon's cell %.1f, radius %g\n",
+            g.count, g.table, used, mx, sizes.empty() ? 0 : sizes[sizes.size() / 2], sizes.empty() ? 0 : sizes[sizes.size() * 99 / 100], g.count ? (double)sq / g.count : 0.0, sqrt(g.radius_sqr));
+}
+
+/* `iterations` progressive iterations (VCMIntegrator::render, vcm.cpp:26-55, once per iteration).  Within one call consecutive
+ * iterations are pipelined (BPT, VCM, PPM): the camera pass of iteration k is enqueued only after the light wavefronts of
+ * iteration k+1, so that it runs on the main stream BESIDE the tail of that light pass (the few paths trapped in glass, one
+ * warp each, latency-bound for ~10 ms at 1080p: vcm.cu) on a side stream.  What a camera pass reads is double-buffered; when
+ * the call returns no camera pass is pending.  IMBA_VCM_NO_PIPELINE=1 (and the sorted order, which shares its scratch
+ * buffers) runs the passes strictly one after the other as the reference does. */
+int imba_vcm_render(imba_integrator* it, int iterations) {
     if (!it->cache_last) { imba_set_error("imba_integrator_preprocess must be called before rendering with a VCM-family integrator"); return IMBA_ERR_INVALID; }
     const int algo = it->cfg.algorithm;
-    const uint64_t global_iter = it->iteration * (uint64_t)it->cfg.rank_count + (uint64_t)it->cfg.rank;
-    // the radius schedule follows the GLOBAL iteration index when iterations are sharded over ranks
-    const VcmParams P = iteration_params(it, global_iter + 1);
-    int rc = set_params(it, P);
-    if (rc != IMBA_OK) return rc;
-    if (algo != IMBA_ALGO_VCM_PT) {
-        rc = light_pass(it, algo, imba_iteration_seed(it->cfg.seed, global_iter, 1), it->cfg.light_path_count, nullptr, !getenv("IMBA_NO_GRAPH"));
-        if (rc != IMBA_OK) return rc;
-        if (algo != IMBA_ALGO_LT) { // light_vertices_.build(pm_radius_, algo != ALGO_BPT), vcm.cpp:98-99
-            IMBA_CUDA(imba_grid_build(it->cache, it->cache_last, it->cache_capacity, P.pm_radius, it->grid, it->grid_bbox, it->cells, it->table, it->block_sums,
-                                      it->photons, it->photon_pos, algo != IMBA_ALGO_BPT, it->stream), IMBA_ERR_CUDA);
-            g_imba_launches.fetch_add(algo != IMBA_ALGO_BPT ? 7 : 1);
-            if (getenv("IMBA_GRID_STATS") && algo != IMBA_ALGO_BPT) { // occupancy of the photon hash grid (diagnosis only)
-                GridParams g; cudaMemcpy(&g, it->grid, sizeof(g), cudaMemcpyDeviceToHost);
-                std::vector<int> ends(g.table);
-                cudaMemcpy(ends.data(), it->cells, sizeof(int) * g.table, cudaMemcpyDeviceToHost);
-                long long used = 0, sq = 0; int mx = 0, prev = 0; std::vector<int> sizes;
-                for (unsigned c = 0; c < g.table; ++c) { const int n = ends[c] - prev; prev = ends[c]; if (n > 0) { ++used; sq += (long long)n * n; mx = std::max(mx, n); sizes.push_back(n); } }
-                std::sort(sizes.begin(), sizes.end());
-                fprintf(stderr, "[imba] photon grid: %d photons, table %u, %lld cells used, largest %d, median %d, p99 %d, mean photons scanned per visited photon's cell %.1f, radius %g\n",
-                        g.count, g.table, used, mx, sizes.empty() ? 0 : sizes[sizes.size() / 2], sizes.empty() ? 0 : sizes[sizes.size() * 99 / 100], g.count ? (double)sq / g.count : 0.0, sqrt(g.radius_sqr));
+    const bool pipelined = it->vset[1].cache != nullptr && !getenv("IMBA_VCM_NO_PIPELINE") && !getenv("IMBA_VCM_SORT");
+    int rc = IMBA_OK;
+    for (int k = 0; k < iterations; ++k, ++it->iteration) {
+        const uint64_t global_iter = it->iteration * (uint64_t)it->cfg.rank_count + (uint64_t)it->cfg.rank;
+        const int b = pipelined ? (int)(it->iteration & 1) : 0;
+        use_set(it, b); use_queues(it, it->light_q);
+        // the radius schedule follows the GLOBAL iteration index when iterations are sharded over ranks
+        const VcmParams P = iteration_params(it, global_iter + 1);
+        if ((rc = set_params(it, P, b)) != IMBA_OK) return rc;
+        if (algo != IMBA_ALGO_VCM_PT) {
+            const bool beside = pipelined && it->camera_pending;
+            rc = light_pass(it, algo, imba_iteration_seed(it->cfg.seed, global_iter, 1), it->cfg.light_path_count, nullptr, !getenv("IMBA_NO_GRAPH"), beside ? it->tail_stream : nullptr);
+            if (rc != IMBA_OK) return rc;
+            if (beside) { // the previous iteration's camera pass, while the tail of this light pass crawls along on the side stream
+                use_set(it, it->pending_set); use_queues(it, it->cam_q);
+                rc = camera_pass(it, algo, it->pending_global_iter);
+                it->camera_pending = false;
+                use_set(it, b); use_queues(it, it->light_q);
+                if (rc != IMBA_OK) return rc;
+                IMBA_CUDA(cudaStreamWaitEvent(it->stream, it->ev_tail_done, 0), IMBA_ERR_CUDA);
+            }
+            if (algo != IMBA_ALGO_LT) { // light_vertices_.build(pm_radius_, algo != ALGO_BPT), vcm.cpp:98-99
+                IMBA_CUDA(imba_grid_build(it->cache, it->cache_last, it->cache_capacity, P.pm_radius, it->grid, it->grid_bbox, it->cells, it->table, it->block_sums,
+                                          it->photons, it->photon_pos, algo != IMBA_ALGO_BPT, it->d_table_state, it->stream), IMBA_ERR_CUDA);
+                g_imba_launches.fetch_add(algo != IMBA_ALGO_BPT ? 7 : 1);
+                if (getenv("IMBA_GRID_STATS") && algo != IMBA_ALGO_BPT) grid_stats(it);
             }
         }
-    }
-    if (algo != IMBA_ALGO_LT) {
-        IMBA_CUDA(imba_vcm_camera_raygen(it->cam, it->d_params, it->cfg.spp, imba_iteration_seed(it->cfg.seed, global_iter, 2), it->pixel_capacity, it->rays[0],
-                                         (VCMState*)it->states[0], it->count[0], it->stream), IMBA_ERR_CUDA);
-        g_imba_launches.fetch_add(1);
-        int cur = 0;
-        for (int wave = 0; wave < it->cfg.max_path_len; ++wave, cur ^= 1) {
-            rc = vcm_wavefront(it, algo, false, cur, it->pixel_capacity, true);
-            if (rc != IMBA_OK) return rc;
+        if (algo != IMBA_ALGO_LT) {
+            if (pipelined && k + 1 < iterations) { it->camera_pending = true; it->pending_set = b; it->pending_global_iter = global_iter; }
+            else {
+                if (pipelined) use_queues(it, it->cam_q);
+                rc = camera_pass(it, algo, global_iter);
+                use_queues(it, it->light_q);
+                if (rc != IMBA_OK) return rc;
+            }
         }
-        IMBA_CUDA(cudaStreamWaitEvent(it->stream, it->ev_shadow_done, 0), IMBA_ERR_CUDA); // framebuffer consumers follow on it->stream
     }
     return IMBA_OK;
 }
@@ -282,7 +374,7 @@ extern "C" int imba_vcm_stage_batch(imba_integrator* it, int stage, int iteratio
         IMBA_CUDA(cudaMemcpyAsync(it->cache_last, &cache_in_count, 4, cudaMemcpyHostToDevice, st), IMBA_ERR_CUDA);
         IMBA_CUDA(cudaStreamSynchronize(st), IMBA_ERR_CUDA);
         IMBA_CUDA(imba_grid_build(it->cache, it->cache_last, it->cache_capacity, P.pm_radius, it->grid, it->grid_bbox, it->cells, it->table, it->block_sums,
-                                  it->photons, it->photon_pos, algo != IMBA_ALGO_BPT && algo != IMBA_ALGO_VCM_PT, st), IMBA_ERR_CUDA);
+                                  it->photons, it->photon_pos, algo != IMBA_ALGO_BPT && algo != IMBA_ALGO_VCM_PT, it->d_table_state, st), IMBA_ERR_CUDA);
     }
     IMBA_CUDA(imba_sort_hits_by_material(it->part, it->hits, S.indices, S.material_count, (int*)it->shadow_states, slots, it->count[0], 0, count, st), IMBA_ERR_CUDA);
     VcmLaunch a = base_launch(it, 0, count);
