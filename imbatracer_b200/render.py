@@ -53,7 +53,7 @@ def main(argv=None):
     ap.add_argument("-c", type=int, default=1); ap.add_argument("-k", type=int, default=10); ap.add_argument("--gamma", type=float, default=0.5)
     ap.add_argument("--seed", type=int, default=1); ap.add_argument("--compare"); ap.add_argument("--help", action="help")
     ap.add_argument("--intermediate-path"); ap.add_argument("--intermediate-time", type=float, default=10.0)
-    ap.add_argument("--iterations-per-pass", type=int, default=1, help="PT: progressive iterations rendered as one wavefront pass (same image)")
+    ap.add_argument("--iterations-per-pass", type=int, default=1, help="progressive iterations per step: PT renders them as one wavefront pass, the bidirectional family pipelines them (same image)")
     a = ap.parse_args(argv)
     if a.s <= 0 and a.t <= 0:
         a.s = 16
@@ -74,7 +74,7 @@ def main(argv=None):
                              iterations_per_pass=a.iterations_per_pass)
     integ = api.Integrator(scene, st)
     integ.preprocess()
-    loop = ProgressiveRenderer(integ, a.w, a.h, a.spp, iterations_per_step=a.iterations_per_pass if a.algo == "pt" else 1)
+    loop = ProgressiveRenderer(integ, a.w, a.h, a.spp, iterations_per_step=a.iterations_per_pass)   # PT: one wavefront pass; BPT / VCM / PPM: pipelined iterations
     t0 = time.time()
     next_dump = a.intermediate_time
     while True:
