@@ -452,9 +452,9 @@ def run_ours(args):
     barrier()
     e2e_s = time.perf_counter() - t0
     # configs[2]: PT 1920x1080 progressive, samples sharded over ranks, one NCCL sum of the float framebuffer per iteration
-    # 4 progressive iterations per wavefront pass (imba_render_settings::iterations_per_pass) and per framebuffer sum; every path
+    # 8 progressive iterations per wavefront pass (imba_render_settings::iterations_per_pass) and per framebuffer sum; every path
     # keeps the seed of its own iteration, the image is that of single passes -- which `pt_single_pass` times for comparison
-    pt = run_pt(scene, flat, rank, world, barrier, dist if world > 1 else None, iters=4 * max(1, min(args.steps // 2, 8)), per_pass=4)
+    pt = run_pt(scene, flat, rank, world, barrier, dist if world > 1 else None, iters=8 * max(1, min(args.steps // 4, 4)), per_pass=8)
     pt_single = run_pt(scene, flat, rank, world, barrier, dist if world > 1 else None, iters=max(4, min(args.steps * 2, 32)))
     # the same with 4 samples per pixel per wavefront pass: larger wavefronts amortise the tails of the late, small waves
     pt_spp4 = run_pt(scene, flat, rank, world, barrier, dist if world > 1 else None, iters=max(2, min(args.steps, 8)), spp=4)
