@@ -722,7 +722,7 @@ cudaError_t imba_vcm_camera_shade(int algo, const VcmLaunch& a, cudaStream_t st)
 cudaError_t imba_vcm_light_tail(int algo, bool masks, const VcmLaunch& a, const TraceArgs& T, int capacity, cudaStream_t st) {
     if (capacity <= 0) return cudaSuccess;
     // stage 1: one thread per path for up to `budget` bounces (most paths end here); stage 2: the survivors, one warp per path
-    const int budget = getenv("IMBA_TAIL_BUDGET") ? atoi(getenv("IMBA_TAIL_BUDGET")) : 24;
+    const int budget = getenv("IMBA_TAIL_BUDGET") ? atoi(getenv("IMBA_TAIL_BUDGET")) : 8;   // sweep 8 / 16 / 24 / 48 on stilllife-proxy LT: 15.2 / 15.5 / 15.8 / 16.6 ms
     const bool two_stage = budget > 0 && a.out_rays && a.out_states && a.out_count;
     const int grid = (capacity + 63) / 64, unlimited = 1 << 20;
     if (two_stage) { const cudaError_t e = cudaMemsetAsync(a.out_count, 0, sizeof(int), st); if (e != cudaSuccess) return e; }
