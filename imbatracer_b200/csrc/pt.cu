@@ -21,8 +21,11 @@ __global__ void pt_raygen_kernel(DevCamera cam, int spp, PtSeeds seeds, int per_
     if (k >= count) return;
     // several progressive iterations may share one pass (imba_render_settings::iterations_per_pass): slot k belongs to
     // iteration k / per_iteration of the group and is seeded exactly as in a pass of its own
-    const int sub = k / per_iteration;
-    const int i = first + k - sub * per_iteration;
+    // interleaved: the paths of one pixel in the `group` iterations sit next to each other in the queue, like the samples of one
+    // pixel with --spp > 1 (more coherent warps than one iteration after the other: +4 % at group 4)
+    const int group = count / per_iteration;
+    const int sub = k % group;
+    const int i = first + k / group;
     const uint32_t seed_base = seeds.base[sub];
     const int pixel_idx = i / spp, sample_idx = i % spp;
     const int y = pixel_idx / cam.width, x = pixel_idx % cam.width;
