@@ -284,15 +284,16 @@ def run_integrators(scene, flat, width=1920, height=1080, iters=4):
     from imbatracer_b200 import api
     out = {}
     for algo in ("bpt", "vcm", "lt", "ppm"):
-        it = api.Integrator(scene, api.render_settings(flat, algo, width, height, seed=5))
-        it.preprocess(); it.render(1); it.sync()
+        # one render(iters) call: BPT / VCM / PPM pipeline the iterations, the light tracer traces their light paths as one pass
+        it = api.Integrator(scene, api.render_settings(flat, algo, width, height, seed=5, iterations_per_pass=iters if algo == "lt" else 1))
+        it.preprocess(); it.render(iters if algo == "lt" else 1); it.sync()
         p0, s0 = it.ray_counts()
         t0 = time.perf_counter(); it.render(iters); it.sync(); dt = time.perf_counter() - t0
         p1, s1 = it.ray_counts()
         img = it.download()
         it.close()
         out[algo] = {"ms_per_iteration": dt / iters * 1e3, "samples_per_s": width * height * iters / dt, "mrays_s": (p1 - p0 + s1 - s0) / dt / 1e6,
-                     "mean_radiance": float(img.mean()) / (iters + 1)}
+                     "mean_radiance": float(img.mean()) / (iters + (iters if algo == "lt" else 1))}
     out["workload"] = f"{width}x{height}, light paths W*H/2, 1 connection, 10 nearest photons, max path length 10, {SCENE}"
     return out
 

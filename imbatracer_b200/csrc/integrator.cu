@@ -64,11 +64,12 @@ extern "C" imba_integrator* imba_integrator_create(imba_scene* scene, const imba
     imba_integrator* it = new imba_integrator;
     it->scene = scene; it->cfg = *s; it->cam = make_camera(*s);
     if (it->cfg.rank_count <= 0) { it->cfg.rank_count = 1; it->cfg.rank = 0; }
-    it->cfg.iterations_per_pass = vcm ? 1 : std::min(std::max(it->cfg.iterations_per_pass, 1), 16);
+    it->cfg.iterations_per_pass = (vcm && s->algorithm != IMBA_ALGO_LT) ? 1 : std::min(std::max(it->cfg.iterations_per_pass, 1), 16);
     it->pixel_capacity = s->width * s->height * s->spp;
     it->state_bytes = vcm ? (int)sizeof(VCMState) : (int)sizeof(PTState);
     it->shadow_slots = vcm ? s->num_connections + 1 : 1;
-    const long long cap = std::max((long long)s->width * s->height * s->spp * it->cfg.iterations_per_pass, vcm ? (long long)s->light_path_count : 0ll);
+    const long long cap = std::max((long long)s->width * s->height * s->spp * (vcm ? 1 : it->cfg.iterations_per_pass),
+                                   vcm ? (long long)s->light_path_count * it->cfg.iterations_per_pass : 0ll);
     if (cap * it->shadow_slots > (1ll << 30)) { imba_set_error("queue capacity too large"); delete it; return nullptr; }
     it->capacity = (int)cap;
     bool ok = cudaStreamCreateWithFlags(&it->stream, cudaStreamNonBlocking) == cudaSuccess;

@@ -31,19 +31,24 @@ __device__ __forceinline__ Bsdf vertex_bsdf(const DeviceShading& S, const DevLig
 }
 
 /* ---- light pass ------------------------------------------------------------------------------------------- */
-__global__ void vcm_light_raygen_kernel(const DeviceShading S, const VcmParams* Pd, uint32_t seed_base, int count, float4* rays, VCMState* states, int* count_out) {
+__global__ void vcm_light_raygen_kernel(const DeviceShading S, const VcmParams* Pd, PtSeeds seeds, int per_iteration, int total, float4* rays, VCMState* states, int* count_out) {
     const VcmParams P = *Pd;
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p == 0) *count_out = count;
-    if (p >= count) return;
+    const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot == 0) *count_out = total;
+    if (slot >= total) return;
+    // the light tracer may trace the light paths of several iterations as one pass (iterations_per_pass): slot -> (iteration of
+    // the group, path of that iteration); everything below is per iteration, as in a pass of its own
+    const int group = total / per_iteration, count = per_iteration;
+    const int p = slot / group;
+    const uint32_t seed_base = seeds.base[slot % group];
     // UniformLightTileGen: path_count / light_count paths per light, the remainder goes to light 0
     const int per = count / S.light_count, first = per + count % S.light_count;
     const int light = (p < first || per == 0) ? 0 : 1 + (p - first) / per;
     Rng rng; rng.s = seed_primary(seed_base, p, p);
     const float pdf_lightpick = 1.0f / S.light_count;
     const EmitSample s = light_sample_emit(S, light, rng);
-    rays[2 * p] = make_float4(s.pos.x, s.pos.y, s.pos.z, 1e-3f);
-    rays[2 * p + 1] = make_float4(s.dir.x, s.dir.y, s.dir.z, FLT_MAX);
+    rays[2 * slot] = make_float4(s.pos.x, s.pos.y, s.pos.z, 1e-3f);
+    rays[2 * slot + 1] = make_float4(s.dir.x, s.dir.y, s.dir.z, FLT_MAX);
     VCMState st;
     st.pixel_id = p; st.light_id = light; st.pad = 0;
     const V3 thr = s.radiance / pdf_lightpick;
@@ -53,7 +58,7 @@ __global__ void vcm_light_raygen_kernel(const DeviceShading S, const VcmParams* 
     st.dVC = s.delta ? 0.0f : s.cos_out / (s.pdf_emit_w * pdf_lightpick);
     st.dVM = st.dVC * P.mis_eta_vc;
     st.rng = rng.s;
-    states[p] = st;
+    states[slot] = st;
 }
 
 /* bounce (vcm.cpp:133-190); returns false when the path ends */
@@ -692,8 +697,8 @@ cudaError_t camera_shade(const VcmLaunch& a, cudaStream_t st) {
 
 } // namespace
 
-cudaError_t imba_vcm_light_raygen(const DeviceShading& S, const VcmParams* P, uint32_t seed_base, int count, float4* rays, VCMState* states, int* count_out, cudaStream_t st) {
-    vcm_light_raygen_kernel<<<(std::max(count, 1) + 255) / 256, 256, 0, st>>>(S, P, seed_base, count, rays, states, count_out);
+cudaError_t imba_vcm_light_raygen(const DeviceShading& S, const VcmParams* P, const PtSeeds& seeds, int per_iteration, int total, float4* rays, VCMState* states, int* count_out, cudaStream_t st) {
+    vcm_light_raygen_kernel<<<(std::max(total, 1) + 255) / 256, 256, 0, st>>>(S, P, seeds, per_iteration, total, rays, states, count_out);
     return cudaGetLastError();
 }
 cudaError_t imba_vcm_camera_raygen(const DevCamera& cam, const VcmParams* P, int spp, uint32_t seed_base, int count, float4* rays, VCMState* states, int* count_out, cudaStream_t st) {

@@ -28,7 +28,7 @@ struct VcmLaunch {
     float4* out_rays; VCMState* out_states; int* out_count; // next wavefront's queue (fused compaction)
 };
 
-cudaError_t imba_vcm_light_raygen(const DeviceShading& S, const VcmParams* P, uint32_t seed_base, int count, float4* rays, VCMState* states, int* count_out, cudaStream_t st);
+cudaError_t imba_vcm_light_raygen(const DeviceShading& S, const VcmParams* P, const PtSeeds& seeds, int per_iteration, int total, float4* rays, VCMState* states, int* count_out, cudaStream_t st);
 cudaError_t imba_vcm_camera_raygen(const DevCamera& cam, const VcmParams* P, int spp, uint32_t seed_base, int count, float4* rays, VCMState* states, int* count_out, cudaStream_t st);
 cudaError_t imba_vcm_light_shade(int algo, const VcmLaunch& a, cudaStream_t st);
 cudaError_t imba_vcm_camera_shade(int algo, const VcmLaunch& a, cudaStream_t st);

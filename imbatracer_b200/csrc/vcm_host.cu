@@ -116,10 +116,10 @@ static int build_tail_graph(imba_integrator* it, int algo) {
 }
 
 /* Traces all light paths of one iteration; returns the number of wavefronts through *waves. */
-static int light_pass(imba_integrator* it, int algo, uint32_t seed_base, int path_count, int* waves, bool use_graph, cudaStream_t tail_stream = nullptr) {
+static int light_pass(imba_integrator* it, int algo, const PtSeeds& seeds, int per_iteration, int path_count, int* waves, bool use_graph, cudaStream_t tail_stream = nullptr) {
     const DeviceShading& S = *imba_shading_view(it->scene);
     IMBA_CUDA(cudaMemsetAsync(it->cache_last, 0, sizeof(int), it->stream), IMBA_ERR_CUDA);
-    IMBA_CUDA(imba_vcm_light_raygen(S, it->d_params, seed_base, path_count, it->rays[0], (VCMState*)it->states[0], it->count[0], it->stream), IMBA_ERR_CUDA);
+    IMBA_CUDA(imba_vcm_light_raygen(S, it->d_params, seeds, per_iteration, path_count, it->rays[0], (VCMState*)it->states[0], it->count[0], it->stream), IMBA_ERR_CUDA);
     g_imba_launches.fetch_add(1);
     // The queue size is read back only every `batch` wavefronts (the grid stays sized for the last known count; kernels on
     // an already empty queue return at once), so long light paths do not cost one host round trip per bounce.
@@ -251,7 +251,8 @@ int imba_vcm_preprocess(imba_integrator* it) {
     it->fb = scratch;
     unsigned long long stats[2];
     IMBA_CUDA(cudaMemcpy(stats, it->d_stats, 16, cudaMemcpyDeviceToHost), IMBA_ERR_CUDA);
-    rc = light_pass(it, IMBA_ALGO_PPM /* cache appends only */, imba_iteration_seed(it->cfg.seed, ~0ull, 3), probes, nullptr, false);
+    PtSeeds probe_seed; probe_seed.base[0] = imba_iteration_seed(it->cfg.seed, ~0ull, 3);
+    rc = light_pass(it, IMBA_ALGO_PPM /* cache appends only */, probe_seed, probes, probes, nullptr, false);
     it->fb = saved_fb; cudaFree(scratch);
     if (rc != IMBA_OK) return rc;
     IMBA_CUDA(cudaMemcpy(it->d_stats, stats, 16, cudaMemcpyHostToDevice), IMBA_ERR_CUDA);
@@ -310,7 +311,13 @@ int imba_vcm_render(imba_integrator* it, int iterations) {
         if ((rc = set_params(it, P, b)) != IMBA_OK) return rc;
         if (algo != IMBA_ALGO_VCM_PT) {
             const bool beside = pipelined && it->camera_pending;
-            rc = light_pass(it, algo, imba_iteration_seed(it->cfg.seed, global_iter, 1), it->cfg.light_path_count, nullptr, !getenv("IMBA_NO_GRAPH"), beside ? it->tail_stream : nullptr);
+            // the light tracer has no camera pass: the light paths of up to iterations_per_pass iterations form ONE pass
+            const int group = algo == IMBA_ALGO_LT ? std::min(std::max(it->cfg.iterations_per_pass, 1), iterations - k) : 1;
+            PtSeeds seeds;
+            for (int g = 0; g < group; ++g)
+                seeds.base[g] = imba_iteration_seed(it->cfg.seed, (it->iteration + g) * (uint64_t)it->cfg.rank_count + (uint64_t)it->cfg.rank, 1);
+            rc = light_pass(it, algo, seeds, it->cfg.light_path_count, it->cfg.light_path_count * group, nullptr, !getenv("IMBA_NO_GRAPH"), beside ? it->tail_stream : nullptr);
+            k += group - 1; it->iteration += group - 1;
             if (rc != IMBA_OK) return rc;
             if (beside) { // the previous iteration's camera pass, while the tail of this light pass crawls along on the side stream
                 use_set(it, it->pending_set); use_queues(it, it->cam_q);
@@ -433,7 +440,8 @@ extern "C" int imba_vcm_raygen_batch(imba_integrator* it, int light, int iterati
     int rc = set_params(it, P);
     if (rc != IMBA_OK) return rc;
     const DeviceShading& S = *imba_shading_view(it->scene);
-    if (light) IMBA_CUDA(imba_vcm_light_raygen(S, it->d_params, seed_base, count, it->rays[0], (VCMState*)it->states[0], it->count[0], it->stream), IMBA_ERR_CUDA);
+    PtSeeds one_seed; one_seed.base[0] = seed_base;
+    if (light) IMBA_CUDA(imba_vcm_light_raygen(S, it->d_params, one_seed, count, count, it->rays[0], (VCMState*)it->states[0], it->count[0], it->stream), IMBA_ERR_CUDA);
     else       IMBA_CUDA(imba_vcm_camera_raygen(it->cam, it->d_params, it->cfg.spp, seed_base, count, it->rays[0], (VCMState*)it->states[0], it->count[0], it->stream), IMBA_ERR_CUDA);
     IMBA_CUDA(cudaMemcpyAsync(h_rays, it->rays[0], (size_t)count * 32, cudaMemcpyDeviceToHost, it->stream), IMBA_ERR_CUDA);
     IMBA_CUDA(cudaMemcpyAsync(h_states, it->states[0], (size_t)count * sizeof(VCMState), cudaMemcpyDeviceToHost, it->stream), IMBA_ERR_CUDA);

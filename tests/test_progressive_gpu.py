@@ -126,15 +126,17 @@ def test_vcm_family_queue_order_equals_sorted_order(algo, monkeypatch):
     assert np.abs(a - b).max() <= 1e-3 * max(1.0, a.max())
 
 
-def test_iterations_per_pass_gives_the_image_of_single_passes():
-    """imba_render_settings::iterations_per_pass: several progressive iterations as one large wavefront pass; every path is
-    seeded as in a pass of its own, so ray counts are identical and the images equal up to the order of the atomic adds."""
+@pytest.mark.parametrize("algo", ["pt", "lt"])
+def test_iterations_per_pass_gives_the_image_of_single_passes(algo):
+    """imba_render_settings::iterations_per_pass: several progressive iterations as one large wavefront pass (PT: camera paths;
+    LT: light paths); every path is seeded as in a pass of its own, so ray counts are identical and the images equal up to the
+    order of the atomic adds."""
     from imbatracer_b200 import api
     flat = load_scene("cornell_specular_front", "gpu")
     sc = api.Scene(flat)
     out = []
     for per_pass in (1, 4, 3):
-        it = api.Integrator(sc, api.render_settings(flat, "pt", 128, 96, seed=4, iterations_per_pass=per_pass))
+        it = api.Integrator(sc, api.render_settings(flat, algo, 128, 96, seed=4, iterations_per_pass=per_pass))
         it.preprocess(); it.render(8)           # 3 does not divide 8: the last group is smaller
         out.append((it.download(), it.ray_counts()))
         it.close()
