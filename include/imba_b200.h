@@ -282,8 +282,9 @@ typedef struct {
     /* image-space sharding for multi-GPU: this rank renders sample slices
      * iteration_index*rank_count + rank of the progressive sequence. */
     int32_t rank, rank_count;
-    /* PT: imba_integrator_render(n) processes up to this many consecutive progressive iterations as ONE wavefront pass of
-     * that many times the rays (0 or 1 = one iteration per pass, the reference's behaviour; at most 16).  Every path keeps the
+    /* PT and LT: imba_integrator_render(n) processes up to this many consecutive progressive iterations as ONE wavefront pass
+     * of that many times the camera paths (PT) / light paths (LT) (0 or 1 = one iteration per pass, the reference's behaviour;
+     * at most 16; ignored by BPT / VCM / PPM, whose iterations are pipelined inside one render(n) call instead).  Every path keeps the
      * seed of its own iteration, so the accumulated image is the same; larger wavefronts amortise the small late waves. */
     int32_t iterations_per_pass;
     int32_t reserved;
