@@ -3,8 +3,10 @@
  * (light_vertices.cpp:15-129, light_vertices.h:70-116).
  *
  * Light pass: ONE wavefront over all light paths (the reference tiles them per light, tile_gen.h:102-177); light paths
- * have no length cap (only Russian roulette ends them, vcm.cpp:133-139), so the host reads the queue size back after
- * every wavefront of the light pass.  The camera pass is capped by max_path_len and is enqueued without host sync.
+ * have no length cap (only Russian roulette ends them, vcm.cpp:133-139), so the host reads the queue size back every 2-16
+ * wavefronts and hands the last <= 128 Ki paths to the per-path tail kernels (vcm.cu).  The camera pass is capped by
+ * max_path_len and is enqueued without host sync.  imba_vcm_render pipelines the iterations of one call: camera pass of
+ * iteration k beside the light-pass tail of iteration k+1 (BPT / VCM / PPM), light paths of several iterations as one pass (LT).
  */
 #include <algorithm>
 #include <vector>
