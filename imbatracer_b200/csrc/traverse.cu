@@ -21,7 +21,10 @@
 
 namespace {
 
-constexpr int      BLOCK_THREADS = 128;
+#ifndef IMBA_BLOCK_THREADS
+#define IMBA_BLOCK_THREADS 128
+#endif
+constexpr int      BLOCK_THREADS = IMBA_BLOCK_THREADS;
 constexpr int      STACK_ENTRIES = IMBA_TRAVERSAL_STACK;
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int      REFILL_LANES = 20; // refill when fewer lanes than this are active
