@@ -27,7 +27,10 @@ namespace {
 constexpr int      BLOCK_THREADS = IMBA_BLOCK_THREADS;
 constexpr int      STACK_ENTRIES = IMBA_TRAVERSAL_STACK;
 constexpr unsigned FULL = 0xffffffffu;
-constexpr int      REFILL_LANES = 20; // refill when fewer lanes than this are active
+#ifndef IMBA_REFILL_LANES
+#define IMBA_REFILL_LANES 20
+#endif
+constexpr int      REFILL_LANES = IMBA_REFILL_LANES; // refill when fewer lanes than this are active
 
 /* MODE 0 = closest hit, 1 = any hit, 2 = any hit fused with process_shadow_rays (integrator.h:49-63): no hit record is
  * written; an unoccluded ray adds its ShadowState throughput to the accumulation buffer; slots whose pixel_id < 0 are skipped. */
