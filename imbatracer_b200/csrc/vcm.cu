@@ -498,6 +498,7 @@ __device__ __forceinline__ int grid_query_fixed(const GridParams& g, const int* 
 /* k-NN search of the camera wavefront as its own pass: light on registers (full occupancy hides the latency of the scattered
  * cell reads), streaming through 16-byte positions; the shading kernel picks the lists up.  Searches are issued for every hit on
  * a non-specular, non-emitting material below the length cap -- a superset of the vertices that merge (vcm.cpp:572-611). */
+template <int K>   // K > 0: candidate list of exactly K entries in registers; 0: any k, list in local memory
 __global__ void __launch_bounds__(256) vcm_merge_query_kernel(const DeviceShading S, const VcmParams* Pd, const float4* rays, const int4* hits, const VCMState* states,
                                                               const int* sorted, const int* hit_count_ptr, const int* queue_count_ptr, const GridParams* gp, const int* cells,
                                                               const float4* photon_pos, int* found_out, int stride) {
@@ -517,8 +518,8 @@ __global__ void __launch_bounds__(256) vcm_merge_query_kernel(const DeviceShadin
         const float4 ro = rays[2 * idx], rd = rays[2 * idx + 1];
         const V3 pos = v3(ro) + __int_as_float(h.z) * v3(rd);      // calc_intersection: pos = org + t * dir
         const GridParams g = *gp;
-        count = k == 10 ? grid_query_fixed<10>(g, cells, g.table, photon_pos, pos, found)      // the reference's default (cmd_line.h)
-                        : grid_query(g, cells, g.table, photon_pos, pos, k, found, dist);
+        count = K > 0 ? grid_query_fixed<(K > 0 ? K : 1)>(g, cells, g.table, photon_pos, pos, found)
+                      : grid_query(g, cells, g.table, photon_pos, pos, k, found, dist);
     }
     found_out[idx] = count;
     for (int j = 0; j < count; ++j) found_out[(size_t)(j + 1) * stride + idx] = found[j];
@@ -686,9 +687,19 @@ template <int ALGO>
 cudaError_t camera_shade(const VcmLaunch& a, cudaStream_t st) {
     if (a.S->env_tex >= 0 && ALGO != IMBA_ALGO_VCM_PT)
         vcm_camera_miss_kernel<ALGO><<<(a.capacity + 255) / 256, 256, 0, st>>>(*a.S, a.rays, a.hits, a.states, a.sorted, a.hit_count_ptr, a.queue_count_ptr, a.fb);
-    if (ALGO == IMBA_ALGO_VCM || ALGO == IMBA_ALGO_PPM)
-        vcm_merge_query_kernel<<<(a.capacity + 255) / 256, 256, 0, st>>>(*a.S, a.P, a.rays, a.hits, a.states, a.sorted, a.hit_count_ptr, a.queue_count_ptr, a.grid, a.cells, a.photon_pos,
-                                                                       a.merge_found, a.merge_stride);
+    if (ALGO == IMBA_ALGO_VCM || ALGO == IMBA_ALGO_PPM) {
+        const int blocks = (a.capacity + 255) / 256;
+#define MERGE_QUERY(KK) vcm_merge_query_kernel<KK><<<blocks, 256, 0, st>>>(*a.S, a.P, a.rays, a.hits, a.states, a.sorted, a.hit_count_ptr, a.queue_count_ptr, a.grid, a.cells, \
+                                                                          a.photon_pos, a.merge_found, a.merge_stride)
+        switch (getenv("IMBA_KNN_GENERIC") ? 0 : a.knn) { // register-resident lists for the usual sizes (10 = the reference's default, cmd_line.h)
+            case 10: MERGE_QUERY(10); break;
+            case 4:  MERGE_QUERY(4); break;
+            case 8:  MERGE_QUERY(8); break;
+            case 16: MERGE_QUERY(16); break;
+            default: MERGE_QUERY(0);
+        }
+#undef MERGE_QUERY
+    }
     vcm_camera_shade_kernel<ALGO><<<(a.capacity + 127) / 128, 128, 0, st>>>(*a.S, a.P, a.rays, a.hits, a.states, a.sorted, a.hit_count_ptr, a.queue_count_ptr, a.shadow_rays,
                                                                            a.shadow_states, a.cache, a.grid, a.cells, a.table, a.photons, a.merge_found, a.merge_stride, a.fb,
                                                                            a.ray_stats, a.out_rays, a.out_states, a.out_count);

@@ -23,7 +23,7 @@ struct VcmLaunch {
     const GridParams* grid; const int* cells; unsigned table; const DevPhoton* photons;
     const float4* photon_pos;   // positions only, in cell order: what the k-NN search streams through
     int* merge_found;           // k-NN results per queue slot: row 0 = count, rows 1..k = photon indices; row stride = merge_stride
-    int merge_stride;
+    int merge_stride; int knn;
     float* fb; unsigned long long* ray_stats;
     float4* out_rays; VCMState* out_states; int* out_count; // next wavefront's queue (fused compaction)
 };

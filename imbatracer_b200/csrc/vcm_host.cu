@@ -37,7 +37,7 @@ static VcmLaunch base_launch(imba_integrator* it, int cur, int capacity, bool so
     a.shadow_rays = it->shadow_rays; a.shadow_states = it->shadow_states;
     a.cache = it->cache; a.cache_capacity = it->cache_capacity; a.cache_last = it->cache_last;
     a.grid = it->grid; a.cells = it->cells; a.table = it->table; a.photons = it->photons;
-    a.photon_pos = it->photon_pos; a.merge_found = it->merge_found; a.merge_stride = it->capacity;
+    a.photon_pos = it->photon_pos; a.merge_found = it->merge_found; a.merge_stride = it->capacity; a.knn = it->cfg.num_knn;
     a.fb = it->fb; a.ray_stats = it->d_stats;
     a.out_rays = it->rays[cur ^ 1]; a.out_states = (VCMState*)it->states[cur ^ 1]; a.out_count = it->count[cur ^ 1];
     return a;
@@ -129,6 +129,7 @@ static int light_pass(imba_integrator* it, int algo, const PtSeeds& seeds, int p
     const int mega = getenv("IMBA_TAIL_PATHS") ? atoi(getenv("IMBA_TAIL_PATHS")) : TAIL_MEGA_PATHS;
     while (n > 0) {
         if (use_graph && n <= mega) { // few paths left: one thread per path follows it to its end (vcm.cu: vcm_light_tail_kernel)
+            IMBA_CUDA(cudaStreamWaitEvent(it->stream, it->ev_shadow_done, 0), IMBA_ERR_CUDA); // last wavefront's shadow traversal reads the queue counts the tail resets
             TraceArgs T; imba_scene_trace_args(it->scene, &T);
             const VcmLaunch a = base_launch(it, cur, n);
             if (tail_stream) { // pipelined: the tail runs beside the previous iteration's camera pass (imba_vcm_render)
@@ -142,6 +143,7 @@ static int light_pass(imba_integrator* it, int algo, const PtSeeds& seeds, int p
         }
         const int tail_rays = std::min(TAIL_RAYS, it->capacity);
         if (use_graph && n <= tail_rays && cur == 0) {
+            IMBA_CUDA(cudaStreamWaitEvent(it->stream, it->ev_shadow_done, 0), IMBA_ERR_CUDA);
             if (!it->tail_graph) { const int rc = build_tail_graph(it, algo); if (rc != IMBA_OK) return rc; }
             IMBA_CUDA(cudaGraphLaunch(it->tail_graph, it->stream), IMBA_ERR_CUDA);
             g_imba_launches.fetch_add(TAIL_WAVES * 6);
@@ -149,7 +151,7 @@ static int light_pass(imba_integrator* it, int algo, const PtSeeds& seeds, int p
         } else {
             const int k_end = (use_graph && n <= tail_rays) ? 1 : batch; // make the parity even before switching to the graph
             for (int k = 0; k < k_end; ++k, cur ^= 1, ++w) {
-                const int rc = vcm_wavefront(it, algo, true, cur, n);
+                const int rc = vcm_wavefront(it, algo, true, cur, n, true);   // camera-connection shadow rays beside the next wave's traversal
                 if (rc != IMBA_OK) return rc;
             }
             if (batch < 16) batch *= 2;
@@ -158,6 +160,7 @@ static int light_pass(imba_integrator* it, int algo, const PtSeeds& seeds, int p
         IMBA_CUDA(cudaStreamSynchronize(it->stream), IMBA_ERR_CUDA);
         if (w > 65536) { imba_set_error("light pass did not terminate"); return IMBA_ERR_OVERFLOW; }
     }
+    IMBA_CUDA(cudaStreamWaitEvent(it->stream, it->ev_shadow_done, 0), IMBA_ERR_CUDA);
     if (waves) *waves = w;
     if (getenv("IMBA_VERBOSE")) fprintf(stderr, "[imba] light pass: %d paths, %d wavefronts\n", path_count, w);
     return IMBA_OK;

@@ -182,3 +182,27 @@ def test_pipelined_iterations_equal_strictly_ordered_iterations(algo, monkeypatc
         else:
             assert counts[0] == ref_counts[0] and abs(counts[1] - ref_counts[1]) <= 2e-3 * ref_counts[1]
             assert abs(img.sum() - ref_img.sum()) <= 0.03 * ref_img.sum()
+
+
+@pytest.mark.parametrize("knn", [4, 8, 10, 16, 7])
+def test_register_resident_knn_lists_equal_the_generic_search(knn, monkeypatch):
+    """vcm_merge_query_kernel<K>: for k = 4, 8, 10, 16 the k nearest photons are kept in registers (grid_query_fixed), any other k
+    (here 7) and IMBA_KNN_GENERIC=1 use the local-memory insertion sort that restates HashGrid::query (rangesearch.h:78-129).
+    Same visiting order and insertion rule, so PPM must give identical ray counts and images."""
+    from imbatracer_b200 import api
+    flat = load_scene("cornell_org", "gpu")
+    sc = api.Scene(flat)
+    out = []
+    for generic in (False, True):
+        if generic:
+            monkeypatch.setenv("IMBA_KNN_GENERIC", "1")
+        else:
+            monkeypatch.delenv("IMBA_KNN_GENERIC", raising=False)
+        it = api.Integrator(sc, api.render_settings(flat, "ppm", 96, 96, seed=3, num_knn=knn))
+        it.preprocess(); it.render(3)
+        out.append((it.download(), it.ray_counts()))
+        it.close()
+    sc.close()
+    (a, ca), (b, cb) = out
+    assert ca == cb and a.sum() > 0
+    assert np.abs(a - b).max() <= 1e-4 * max(1.0, a.max())
