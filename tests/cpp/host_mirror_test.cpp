@@ -13,7 +13,11 @@ int main() {
     MyState s = { 7, 0, 42ull };
     q.push(r, s);
     if (q.size() != 1 || q.states()[0].pixel_id != 7) return 11;
+    imba_render_settings rs = imba_b200::default_settings(64, 48);
+    rs.iterations_per_pass = 4;                       // PT / LT: four progressive iterations per wavefront pass
+    if (rs.spp != 1 || rs.max_path_len != 10 || rs.light_path_count != 64 * 48 / 2 || sizeof(rs) % 8 != 0) return 13;
     imba_scene_desc d; std::memset(&d, 0, sizeof(d));
+    d.accel_layout = IMBA_ACCEL_DEVICE_BUILD;         // the enumerator must exist for C++ hosts too
     try {
         imba_b200::Scene scene(d);
         std::printf("scene created\n");
