@@ -257,6 +257,17 @@ int imba_scene_build_accel_device(imba_scene* s, const imba_scene_desc* d, float
         if (n <= 0) { imba_set_error("mesh %d has no triangles", mi); return IMBA_ERR_INVALID; }
         node_cap += (size_t)std::max(n - 1, 1);
     }
+    // the kernels index the vertex array with what the index array says: reject anything out of range here
+    for (int mi = 0; mi < d->mesh_count; ++mi) {
+        const int nvm = d->mesh_vertex_base[mi + 1] - d->mesh_vertex_base[mi];
+        for (int t = d->mesh_tri_base[mi]; t < d->mesh_tri_base[mi + 1]; ++t)
+            for (int c = 0; c < 3; ++c) {
+                const int v = d->indices[4 * (size_t)t + c];
+                if (v < 0 || v >= nvm) { imba_set_error("triangle %d of mesh %d refers to vertex %d (mesh has %d)", t - d->mesh_tri_base[mi], mi, v, nvm); return IMBA_ERR_INVALID; }
+            }
+    }
+    for (int i = 0; i < d->instance_count; ++i)
+        if (d->instances[i].mesh_id < 0 || d->instances[i].mesh_id >= d->mesh_count) { imba_set_error("instance %d refers to mesh %d", i, d->instances[i].mesh_id); return IMBA_ERR_INVALID; }
     DeviceBuf d_vertices, d_indices, d_nodes, d_tris, d_work, d_ctr;
     BG_CUDA(d_vertices.alloc((size_t)nv * 16)); BG_CUDA(d_indices.alloc((size_t)nt_all * 16));
     BG_CUDA(cudaMemcpy(d_vertices.p, d->vertices, (size_t)nv * 16, cudaMemcpyHostToDevice));

@@ -179,3 +179,18 @@ def test_device_built_structure_gives_identical_traversal_results(scenes, name, 
         assert np.isfinite(img).all() and img.sum() > 0
     finally:
         sc.close()
+
+
+@pytest.mark.gpu
+def test_device_build_rejects_out_of_range_indices():
+    """The device builder's kernels index the vertex array with the index array: bad input must be refused on the host."""
+    from imbatracer_b200 import api
+    s = procedural.terrain(4)
+    idx = s.arrays["indices"].reshape(-1, 4)
+    idx[5, 1] = 10_000_000
+    with pytest.raises(RuntimeError, match="refers to vertex"):
+        api.Scene(s, device_build=True)
+    idx[5, 1] = 0
+    s.arrays["instances"]["mesh_id"][0] = 3
+    with pytest.raises(RuntimeError, match="refers to mesh"):
+        api.Scene(s, device_build=True)
