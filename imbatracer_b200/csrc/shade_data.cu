@@ -21,6 +21,17 @@ static const T* up(ShadingStorage* st, const void* src, size_t count, bool& ok) 
 }
 
 int imba_shading_upload(imba_scene* s, const imba_scene_desc* d) {
+    // the shading kernels follow these indices on the device: refuse anything out of range here (the reference trusts its loader)
+    for (int mi = 0; mi < d->mesh_count; ++mi) {
+        const int nvm = d->mesh_vertex_base[mi + 1] - d->mesh_vertex_base[mi];
+        for (int t = d->mesh_tri_base[mi]; t < d->mesh_tri_base[mi + 1]; ++t) {
+            const int32_t* q = d->indices + 4 * (size_t)t;
+            if (q[0] < 0 || q[0] >= nvm || q[1] < 0 || q[1] >= nvm || q[2] < 0 || q[2] >= nvm) { imba_set_error("triangle %d of mesh %d refers to a vertex outside the mesh (%d vertices)", t - d->mesh_tri_base[mi], mi, nvm); return IMBA_ERR_INVALID; }
+            if (d->materials && (q[3] < 0 || q[3] >= d->material_count)) { imba_set_error("triangle %d of mesh %d refers to material %d (%d materials)", t - d->mesh_tri_base[mi], mi, q[3], d->material_count); return IMBA_ERR_INVALID; }
+        }
+    }
+    for (int i = 0; i < d->instance_count; ++i)
+        if (d->instances[i].mesh_id < 0 || d->instances[i].mesh_id >= d->mesh_count) { imba_set_error("instance %d refers to mesh %d", i, d->instances[i].mesh_id); return IMBA_ERR_INVALID; }
     ShadingStorage* st = new ShadingStorage;
     memset(&st->view, 0, sizeof(st->view));
     s->shading = reinterpret_cast<DeviceShading*>(st);
