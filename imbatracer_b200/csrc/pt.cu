@@ -1,9 +1,11 @@
 /* pt.cu -- path-tracer wavefront stages on the device.
  *   pt_raygen_kernel   PixelRayGen::fill_queue + PathTracer::render's sample function (ray_gen.h:36-80, pt.cpp:168-177,
- *                      camera.h:57-65)
- *   pt_shade_kernel    PathTracer::process_primary_rays / compute_direct_illum / bounce (pt.cpp:82-160, 17-44, 46-80)
- *                      on material-sorted hit indices; the shadow ray of slot i is written to slot i of the shadow
- *                      queue (no atomic push), continuation rays overwrite the slot in place like the reference
+ *                      camera.h:57-65); the paths of several progressive iterations may share one pass (iterations_per_pass)
+ *   pt_shade_kernel    PathTracer::process_primary_rays / compute_direct_illum / bounce (pt.cpp:82-160, 17-44, 46-80),
+ *                      in queue order (the integrator's default) or on material-sorted hit indices (the reference's order:
+ *                      parity harness, IMBA_PT_SORT=1); the shadow ray of slot i is written to slot i of the shadow queue (no
+ *                      atomic push), survivors are pushed into the next queue (or overwrite their slot in the harness path)
+ *   pt_miss_kernel     environment map for the rays that left the scene (pt.cpp:95-116)
  *   pixel-size probe   Integrator::estimate_pixel_size (integrator.cpp:14-71)
  */
 #include "integrator.cuh"

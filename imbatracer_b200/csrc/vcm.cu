@@ -7,6 +7,8 @@
  *   vcm_camera_raygen   trace_camera_paths' sample function                                       vcm.cpp:109-129
  *   vcm_camera_shade    process_camera_rays, direct_illum, connect, vertex_merging, bounce        vcm.cpp:323-439, 442-486, 489-569, 572-611
  *   grid_*              HashGrid::build (bbox, count, scan, scatter) and ::query (8 cells, k-NN)  rangesearch.h:25-129
+ *   vcm_merge_query     the k-NN search of a camera wavefront as its own pass (lists in registers for k = 4, 8, 10, 16)
+ *   vcm_light_tail*     the last <= 128 Ki light paths: one thread, then one warp per path (trace_single / trace_warp)
  * mis_pow(a) = powf(a, 1) = a (vcm.h:112-115) is applied as the identity.
  */
 #include "integrator.cuh"
