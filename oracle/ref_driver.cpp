@@ -529,6 +529,35 @@ int ref_scene_add_test_envmap(void* h, uint64_t seed, float intensity) {
     return 1;
 }
 
+
+/// Start of the light paths: the sample function VCMIntegrator::trace_light_paths hands to its ray generator (vcm.cpp:64-96),
+/// i.e. Light::sample_emit of the reference's lights (light.h) + the initial partial MIS weights, for given (light, RNG state)
+/// pairs -- the seeding itself (ray_gen.h:122-152) is covered by ref_seed_states.  The few assignments of that lambda are
+/// restated here because it cannot be called outside run_iteration; all arithmetic is the reference's sample_emit.
+int ref_vcm_light_emit(void* h, int count, const int* light_ids, const uint64_t* rng_in, float mis_eta_vc, imba_ray* rays_out, void* states_out) {
+    auto rs = (RefScene*)h; Scene& scene = *rs->scene;
+    VCMState* out = (VCMState*)states_out;
+    const float pdf_lightpick = 1.0f / scene.light_count();
+    for (int i = 0; i < count; ++i) {
+        if (light_ids[i] < 0 || light_ids[i] >= (int)scene.light_count()) return -1;
+        VCMState st; memset(&st, 0, sizeof(st));
+        st.ray_id = i; st.light_id = light_ids[i]; st.rng.state_ = rng_in[i];
+        auto& l = scene.light(light_ids[i]);
+        Light::EmitSample sample = l->sample_emit(st.rng);
+        ::Ray r;
+        r.org.x = sample.pos.x; r.org.y = sample.pos.y; r.org.z = sample.pos.z; r.org.w = 1e-3f;
+        r.dir.x = sample.dir.x; r.dir.y = sample.dir.y; r.dir.z = sample.dir.z; r.dir.w = FLT_MAX;
+        st.throughput = sample.radiance / pdf_lightpick;
+        st.path_length = 1;
+        st.dVCM = sample.pdf_direct_a / sample.pdf_emit_w;
+        st.dVC = l->is_delta() ? 0.0f : sample.cos_out / (sample.pdf_emit_w * pdf_lightpick);
+        st.dVM = st.dVC * mis_eta_vc;
+        st.finite_light = l->is_finite();
+        memcpy(&rays_out[i], &r, 32); out[i] = st;
+    }
+    return 0;
+}
+
 /// RNG known-answer helper (render/random.h:15-47).
 void ref_rng_floats(uint64_t seed, int discard, int n, float* out, uint64_t* state_out) {
     RNG rng(seed); rng.discard(discard);

@@ -61,6 +61,7 @@ def ref():
         L.ref_rng_floats.restype = None; L.ref_rng_floats.argtypes = [C.c_uint64, i32, i32, vp, vp]
         L.ref_seed_states.restype = None; L.ref_seed_states.argtypes = [C.c_uint64, i32, i32, i32, vp]
         L.ref_struct_sizes.argtypes = [vp]
+        L.ref_vcm_light_emit.argtypes = [vp, i32, vp, vp, f32, vp, vp]
         L.ref_scene_add_test_textures.argtypes = [vp, C.c_uint64]
         L.ref_scene_add_test_envmap.argtypes = [vp, C.c_uint64, f32]
         L.ref_vcm_stage.argtypes = [vp, i32, i32, i32, f32, i32, i32, i32, i32, f32, i32, i32, i32, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp]
@@ -196,6 +197,15 @@ class RefScene:
                                radius_factor, img.ctypes.data, stats.ctypes.data, C.byref(secs), C.byref(px))
         assert rc == 0
         return img, {"primary_rays": int(stats[0]), "shadow_rays": int(stats[1]), "seconds": secs.value, "pixel_size": px.value}
+
+    def light_emit(self, light_ids, rng_states, mis_eta_vc):
+        """Light::sample_emit + initial VCM weights of the reference for (light, RNG state) pairs (ref_driver.cpp: ref_vcm_light_emit)."""
+        n = len(light_ids)
+        light_ids = np.ascontiguousarray(light_ids, np.int32); rng_states = np.ascontiguousarray(rng_states, np.uint64)
+        rays = np.zeros(n, abi.RAY); states = np.zeros(n, abi.VCM_STATE)
+        rc = self.L.ref_vcm_light_emit(self.h, n, light_ids.ctypes.data, rng_states.ctypes.data, mis_eta_vc, rays.ctypes.data, states.ctypes.data)
+        assert rc == 0
+        return rays, states
 
     def pt_shade_batch(self, w, h, rays, hits, states, fov=60.0, max_path_len=10):
         """PathTracer::process_primary_rays (pt.cpp:82-160) of the reference on an injected batch."""

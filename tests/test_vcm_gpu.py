@@ -131,3 +131,61 @@ def test_vcm_stages_with_environment_light(algo):
             assert c["same_order"] and c["rng_equal"] == 1.0 and c["len_equal"] == 1.0 and c["close"] >= 0.998, r
     for r in res["camera"]:
         assert r["fb_rel_err"] < 2e-3 and r["fb_ref_sum"] > 0, r
+
+
+def _all_light_kinds_scene():
+    """cornell_org plus a point, a spot and a directional light (scene-file grammar of build_scene.cpp:380-450), written next to
+    the scratch copy of the Cornell scenes; with the procedural environment map that makes all five light kinds."""
+    path = os.path.join(refapi.REF_SCENES, "cornell", "cornell_lights.scene")
+    if not os.path.exists(path):
+        with open(refapi.scene_path("cornell_org")) as f:
+            text = f.read()
+        text += "\npoint_light 0.3 1.2 0.1  4 3.5 3\nspot_light -0.4 1.5 0.2  0.2 -1 0.1  35  6 6 5\ndir_light 0.3 -1 -0.2  1.5 1.4 1.2\n"
+        with open(path, "w") as f:
+            f.write(text)
+    return path
+
+
+@needs_ref
+@pytest.mark.parametrize("scene", ["cornell_org", "stilllife_proxy", "all_light_kinds"])
+def test_light_path_starts_match_reference_emission_sampling(scene):
+    """The first vertex of the light paths: our generator (vcm_light_raygen_kernel: UniformLightTileGen's light choice, seeding,
+    light_sample_emit, initial dVCM / dVC / dVM) against the reference's Light::sample_emit (light.h) driven with the same
+    (light, RNG state) pairs -- triangle lights, and in the third scene also point, spot, directional and environment lights."""
+    from imbatracer_b200 import abi, api
+    if scene == "all_light_kinds":
+        rs = refapi.RefScene(_all_light_kinds_scene(), True)
+        rs.add_test_envmap(5, 0.7)
+    else:
+        rs = refapi.RefScene(refapi.scene_path(scene), True)
+    flat = rs.flat(scene)
+    kinds = set(int(k) for k in flat.lights["kind"])
+    assert kinds == ({0, 1, 2, 3, 4} if scene == "all_light_kinds" else {0})
+    sc = api.Scene(flat)
+    n = 20000
+    light_paths = 30000
+    it = api.Integrator(sc, api.render_settings(flat, "vcm", 64, 64, light_path_count=light_paths, seed=5))
+    it.preprocess()
+    base_radius, iteration, seed_base = 0.02, 3, 0x51F15EED
+    rays, states = it.vcm_raygen_batch(True, iteration, base_radius, seed_base, n)
+    it.close(); sc.close()
+    rng0 = np.zeros(n, np.uint64)
+    abi.check(abi.lib().imba_seed_states(seed_base, 0, n, 1, rng0.ctypes.data))
+    f32 = np.float32
+    pm_radius = max(f32(base_radius) / f32(np.power(f32(iteration), f32(0.5 * (1.0 - 0.75)))), f32(1e-7))
+    mis_eta_vc = float(f32(1.0) / (f32(np.pi) * pm_radius * pm_radius * f32(light_paths)))
+    ref_rays, ref_states = rs.light_emit(states["light_id"], rng0, mis_eta_vc)
+    rs.close()
+    # every light gets its share of the paths (UniformLightTileGen, tile_gen.h:139-158)
+    assert set(states["light_id"].tolist()) == set(range(len(flat.lights)))
+    assert np.array_equal(states["rng"], ref_states["rng"])                       # same number of random draws, same order
+    assert np.array_equal(states["len_finite"], ref_states["len_finite"])         # path length 1 + finite-light flag
+
+    def close(a, b, tol=2e-5):
+        a, b = a.astype(np.float64), b.astype(np.float64)
+        return np.abs(a - b) <= tol * np.maximum(1.0, np.maximum(np.abs(a), np.abs(b)))
+    assert close(rays["org"], ref_rays["org"]).all() and close(rays["dir"], ref_rays["dir"]).all()
+    assert np.array_equal(rays["tmin"], ref_rays["tmin"]) and np.array_equal(rays["tmax"], ref_rays["tmax"])
+    for k in ("throughput", "dVCM", "dVC"):
+        assert close(states[k], ref_states[k], 1e-4).all(), k
+    assert close(states["dVM"], ref_states["dVM"], 1e-3).all()                    # carries mis_eta_vc, recomputed here in numpy
