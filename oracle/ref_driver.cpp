@@ -558,6 +558,32 @@ int ref_vcm_light_emit(void* h, int count, const int* light_ids, const uint64_t*
     return 0;
 }
 
+/// Start of the camera paths: the sample function of VCMIntegrator::trace_camera_paths (vcm.cpp:109-129) for given pixels and
+/// RNG states -- the reference's camera (camera.h:57-65) and the conversion of the image-plane pdf that initialises dVCM.
+int ref_vcm_camera_start(void* h, int w, int hgt, float fov, int light_path_count, int count, const int* pixel_ids, const uint64_t* rng_in,
+                         imba_ray* rays_out, void* states_out) {
+    auto rs = (RefScene*)h;
+    PerspectiveCamera cam(w, hgt, fov);
+    setup_camera(cam, rs->cam_pos, rs->cam_dir, rs->cam_up);
+    VCMState* out = (VCMState*)states_out;
+    for (int i = 0; i < count; ++i) {
+        VCMState st; memset(&st, 0, sizeof(st));
+        st.pixel_id = pixel_ids[i]; st.rng.state_ = rng_in[i];
+        const int x = pixel_ids[i] % w, y = pixel_ids[i] / w;
+        const float sample_x = static_cast<float>(x) + st.rng.random_float();
+        const float sample_y = static_cast<float>(y) + st.rng.random_float();
+        ::Ray r = cam.generate_ray(sample_x, sample_y);
+        st.throughput = rgb(1.0f);
+        st.path_length = 1;
+        const float3 dir(r.dir.x, r.dir.y, r.dir.z);
+        const float cos_theta_o = dot(dir, cam.dir());
+        const float pdf_cam_w = sqr(cam.image_plane_dist() / cos_theta_o) / cos_theta_o;
+        st.dVC = 0.0f; st.dVM = 0.0f; st.dVCM = light_path_count / pdf_cam_w;
+        memcpy(&rays_out[i], &r, 32); out[i] = st;
+    }
+    return 0;
+}
+
 /// RNG known-answer helper (render/random.h:15-47).
 void ref_rng_floats(uint64_t seed, int discard, int n, float* out, uint64_t* state_out) {
     RNG rng(seed); rng.discard(discard);

@@ -62,6 +62,7 @@ def ref():
         L.ref_seed_states.restype = None; L.ref_seed_states.argtypes = [C.c_uint64, i32, i32, i32, vp]
         L.ref_struct_sizes.argtypes = [vp]
         L.ref_vcm_light_emit.argtypes = [vp, i32, vp, vp, f32, vp, vp]
+        L.ref_vcm_camera_start.argtypes = [vp, i32, i32, f32, i32, i32, vp, vp, vp, vp]
         L.ref_scene_add_test_textures.argtypes = [vp, C.c_uint64]
         L.ref_scene_add_test_envmap.argtypes = [vp, C.c_uint64, f32]
         L.ref_vcm_stage.argtypes = [vp, i32, i32, i32, f32, i32, i32, i32, i32, f32, i32, i32, i32, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp]
@@ -204,6 +205,15 @@ class RefScene:
         light_ids = np.ascontiguousarray(light_ids, np.int32); rng_states = np.ascontiguousarray(rng_states, np.uint64)
         rays = np.zeros(n, abi.RAY); states = np.zeros(n, abi.VCM_STATE)
         rc = self.L.ref_vcm_light_emit(self.h, n, light_ids.ctypes.data, rng_states.ctypes.data, mis_eta_vc, rays.ctypes.data, states.ctypes.data)
+        assert rc == 0
+        return rays, states
+
+    def camera_start(self, w, h, light_path_count, pixel_ids, rng_states, fov=60.0):
+        """Camera-path start of the reference's VCM integrator for (pixel, RNG state) pairs (ref_driver.cpp: ref_vcm_camera_start)."""
+        n = len(pixel_ids)
+        pixel_ids = np.ascontiguousarray(pixel_ids, np.int32); rng_states = np.ascontiguousarray(rng_states, np.uint64)
+        rays = np.zeros(n, abi.RAY); states = np.zeros(n, abi.VCM_STATE)
+        rc = self.L.ref_vcm_camera_start(self.h, w, h, fov, light_path_count, n, pixel_ids.ctypes.data, rng_states.ctypes.data, rays.ctypes.data, states.ctypes.data)
         assert rc == 0
         return rays, states
 

@@ -189,3 +189,29 @@ def test_light_path_starts_match_reference_emission_sampling(scene):
     for k in ("throughput", "dVCM", "dVC"):
         assert close(states[k], ref_states[k], 1e-4).all(), k
     assert close(states["dVM"], ref_states["dVM"], 1e-3).all()                    # carries mis_eta_vc, recomputed here in numpy
+
+
+@needs_ref
+def test_camera_path_starts_match_reference():
+    """The first vertex of the camera paths of the VCM family (vcm_camera_raygen_kernel) against the sample function of the
+    reference's trace_camera_paths (vcm.cpp:109-129): jittered raster position, camera ray, throughput 1, dVC = dVM = 0 and
+    dVCM = light_path_count / pdf_cam_w."""
+    from imbatracer_b200 import abi, api
+    w, h, light_paths, seed_base = 80, 60, 12345, 0x0C0FFEE1
+    rs = refapi.RefScene(refapi.scene_path("cornell_org"), True)
+    flat = rs.flat("cornell_org")
+    sc = api.Scene(flat)
+    it = api.Integrator(sc, api.render_settings(flat, "vcm", w, h, light_path_count=light_paths, seed=5))
+    it.preprocess()
+    rays, states = it.vcm_raygen_batch(False, 2, 0.02, seed_base, w * h)
+    it.close(); sc.close()
+    rng0 = np.zeros(w * h, np.uint64)
+    abi.check(abi.lib().imba_seed_states(seed_base, 0, w * h, 1, rng0.ctypes.data))
+    ref_rays, ref_states = rs.camera_start(w, h, light_paths, states["pixel_id"], rng0)
+    rs.close()
+    assert np.array_equal(states["pixel_id"], np.arange(w * h))
+    assert np.array_equal(states["rng"], ref_states["rng"]) and np.array_equal(states["len_finite"], ref_states["len_finite"])
+    assert np.array_equal(rays["org"], ref_rays["org"]) and np.abs(rays["dir"] - ref_rays["dir"]).max() < 5e-6
+    assert np.array_equal(states["throughput"], ref_states["throughput"])
+    assert (states["dVC"] == 0).all() and (states["dVM"] == 0).all()
+    assert np.allclose(states["dVCM"], ref_states["dVCM"], rtol=2e-5, atol=0)
