@@ -122,6 +122,10 @@ class Integrator:
     def clear(self):
         abi.check(self.L.imba_integrator_clear(self.h), "imba_integrator_clear")
 
+    def reset(self):
+        """Integrator::reset (integrator.h:31, vcm.h:69-72): the progressive sequence (seeds, PPM / VCM radius schedule) starts over."""
+        abi.check(self.L.imba_integrator_reset(self.h), "imba_integrator_reset")
+
     def set_framebuffer(self, tensor):
         assert tensor.is_cuda and tensor.dtype.is_floating_point and tensor.numel() == self.settings.width * self.settings.height * 3
         self._fb = tensor
