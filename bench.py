@@ -236,7 +236,7 @@ def run_reference(args):
             "cpu_baseline": {"value": v, "unit": "Mrays/s", "cores": cores, "kind": "port",
                              "sample": f"4 batches x {n} rays per step (oracle/traversal_oracle.cpp on the reference BVH2 layout; the AnyDSL kernels are not in the reference tree)"},
             "e2e": {"value": v, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(flat, n):
@@ -508,7 +508,28 @@ def run_ours(args):
     if world > 1:
         dist.barrier(); dist.destroy_process_group()
     if line is not None:
-        print(json.dumps(line), flush=True)
+        emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Library chatter (NCCL prints its version line with printf) must not land on stdout beside the ONE JSON line: everything
+    written to file descriptor 1 while the bench runs goes to stderr; emit() writes the line to the real stdout."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    text = json.dumps(line) + "\n"
+    if _REAL_STDOUT is None:
+        sys.stdout.write(text); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, text.encode())
 
 
 def main():
@@ -518,6 +539,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     args = ap.parse_args()
+    quiet_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:
