@@ -117,7 +117,7 @@ int imba_scene_trace_ex(imba_scene* s, const TraceRequest& rq, cudaStream_t stre
     const bool masks = s->has_masks, stats = rq.d_counters != nullptr;
     const int variant = rq.mode * 4 + (masks ? 2 : 0) + (stats ? 1 : 0);
     if (s->grid_cache[variant] == 0) {
-        const int per_sm = imba_trace_blocks_per_sm(rq.mode, masks, stats);
+        const int per_sm = imba_trace_blocks_per_sm(rq.mode, masks, stats, s->flat_inst >= 0);
         if (per_sm <= 0) { imba_set_error("traversal kernel cannot be resident (occupancy 0): %s", cudaGetErrorString(cudaGetLastError())); return IMBA_ERR_CUDA; }
         s->grid_cache[variant] = per_sm * s->sm_count;
     }

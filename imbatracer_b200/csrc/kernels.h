@@ -33,7 +33,7 @@ struct TraceArgs {
 
 int         imba_trace_block_threads();
 /* mode: 0 closest hit, 1 any hit, 2 any hit + shadow resolve */
-int         imba_trace_blocks_per_sm(int mode, bool masks, bool stats);
+int         imba_trace_blocks_per_sm(int mode, bool masks, bool stats, bool flat);
 cudaError_t imba_launch_trace(const TraceArgs& a, int mode, bool masks, bool stats, int grid, cudaStream_t s);
 
 #endif

@@ -31,6 +31,9 @@ constexpr unsigned FULL = 0xffffffffu;
 #define IMBA_REFILL_LANES 20
 #endif
 constexpr int      REFILL_LANES = IMBA_REFILL_LANES; // refill when fewer lanes than this are active
+#ifndef IMBA_SMEM_STACK
+#define IMBA_SMEM_STACK 0  /* traversal-stack entries per thread kept in shared memory (tuning switch) */
+#endif
 
 /* MODE 0 = closest hit, 1 = any hit, 2 = any hit fused with process_shadow_rays (integrator.h:49-63): no hit record is
  * written; an unoccluded ray adds its ShadowState throughput to the accumulation buffer; slots whose pixel_id < 0 are skipped. */
@@ -48,7 +51,18 @@ __global__ void __launch_bounds__(BLOCK_THREADS) trace_kernel(const TraceArgs P)
     const uint4*  __restrict__ nodes = P.nodes;
     const float4* __restrict__ tris  = P.tris;
 
+#if IMBA_SMEM_STACK > 0
+    // the top IMBA_SMEM_STACK entries of the traversal stack live in shared memory ([entry][thread]: conflict-free 64-bit accesses),
+    // deeper ones in the local-memory frame
+    __shared__ uint2 s_stack[IMBA_SMEM_STACK * BLOCK_THREADS];
+    uint2 stack[STACK_ENTRIES > IMBA_SMEM_STACK ? STACK_ENTRIES - IMBA_SMEM_STACK : 1];
+#define STACK_PUSH(e) do { if (sp < IMBA_SMEM_STACK) s_stack[sp * BLOCK_THREADS + threadIdx.x] = (e); else stack[sp - IMBA_SMEM_STACK] = (e); ++sp; } while (0)
+#define STACK_POP()   (--sp, sp < IMBA_SMEM_STACK ? s_stack[sp * BLOCK_THREADS + threadIdx.x] : stack[sp - IMBA_SMEM_STACK])
+#else
     uint2 stack[STACK_ENTRIES];
+#define STACK_PUSH(e) (stack[sp++] = (e))
+#define STACK_POP()   (stack[--sp])
+#endif
     int sp = 0;
     RayRegs r;
     float tmin = 0.0f;
@@ -97,7 +111,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS) trace_kernel(const TraceArgs P)
                 const uint32_t hits = ngroup.y;
                 const uint32_t bit = 31u - (uint32_t)__clz(hits);
                 ngroup.y &= ~(1u << bit);
-                if (ngroup.y > 0x00ffffffu) { stack[sp++] = ngroup; if (STATS) st_sp = max(st_sp, (uint32_t)sp); }
+                if (ngroup.y > 0x00ffffffu) { STACK_PUSH(ngroup); if (STATS) st_sp = max(st_sp, (uint32_t)sp); }
                 const uint32_t slot = (bit - 24u) ^ (r.octinv4 & 0xffu);
                 const uint32_t rel  = __popc(hits & 0xffu & ~(0xffffffffu << slot));
                 const uint4* np = nodes + (size_t)(ngroup.x + rel) * 5;
@@ -119,9 +133,9 @@ __global__ void __launch_bounds__(BLOCK_THREADS) trace_kernel(const TraceArgs P)
                 tgroup.y &= ~(1u << bit);
                 if (cur_inst < 0) {
                     // top level: enter the instance (ray * inverse transform, cpu_adapter.cpp:356-365)
-                    if (ngroup.y > 0x00ffffffu) stack[sp++] = ngroup;
-                    if (tgroup.y != 0) stack[sp++] = tgroup;
-                    stack[sp++] = make_uint2(0xffffffffu, 0u);
+                    if (ngroup.y > 0x00ffffffu) STACK_PUSH(ngroup);
+                    if (tgroup.y != 0) STACK_PUSH(tgroup);
+                    STACK_PUSH(make_uint2(0xffffffffu, 0u));
                     if (STATS) { st_sp = max(st_sp, (uint32_t)sp); ++st_insts; }
                     const float4* ip = P.insts + (size_t)(tgroup.x + bit) * 4;
                     const float4 m0 = __ldg(ip), m1 = __ldg(ip + 1), m2 = __ldg(ip + 2);
@@ -143,7 +157,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS) trace_kernel(const TraceArgs P)
             if (!done && ngroup.y <= 0x00ffffffu && tgroup.y == 0) {
                 for (;;) {
                     if (sp == 0) { done = true; break; }
-                    const uint2 e = stack[--sp];
+                    const uint2 e = STACK_POP();
                     if (e.y == 0u) { // sentinel: leave the instance, restore the world-space ray
                         const float4 o = __ldg(P.rays + 2 * ray_idx), d = __ldg(P.rays + 2 * ray_idx + 1);
                         r.ox = o.x; r.oy = o.y; r.oz = o.z; r.dx = d.x; r.dy = d.y; r.dz = d.z; r.finish();
@@ -178,16 +192,34 @@ __global__ void __launch_bounds__(BLOCK_THREADS) trace_kernel(const TraceArgs P)
     }
 }
 
+
+#undef STACK_PUSH
+#undef STACK_POP
+
+#ifdef IMBA_COOP_TRACE
+#include "traverse_coop.cuh"
+#endif
+
 template <int ANY, bool MASKS, bool STATS>
 cudaError_t launch(const TraceArgs& a, int grid, cudaStream_t s) {
+#ifndef IMBA_COOP_TRACE
     trace_kernel<ANY, MASKS, STATS><<<grid, BLOCK_THREADS, 0, s>>>(a);
+#else
+    const int smem = (BLOCK_THREADS / 32) * (a.flat_inst >= 0 ? COOP_WARP_BYTES_FLAT : COOP_WARP_BYTES_INST);
+    trace_coop_kernel<ANY, MASKS, STATS><<<grid, BLOCK_THREADS, smem, s>>>(a);
+#endif
     return cudaGetLastError();
 }
 
 template <int ANY, bool MASKS, bool STATS>
-int occupancy() {
+int occupancy(bool flat) {
     int n = 0;
+#ifndef IMBA_COOP_TRACE
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, trace_kernel<ANY, MASKS, STATS>, BLOCK_THREADS, 0);
+#else
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, trace_coop_kernel<ANY, MASKS, STATS>, BLOCK_THREADS,
+                                                  (BLOCK_THREADS / 32) * (flat ? COOP_WARP_BYTES_FLAT : COOP_WARP_BYTES_INST));
+#endif
     return n;
 }
 
@@ -200,8 +232,8 @@ int imba_trace_block_threads() { return BLOCK_THREADS; }
     X(1, false, false) X(1, false, true) X(1, true, false) X(1, true, true) \
     X(2, false, false) X(2, true, false)
 
-int imba_trace_blocks_per_sm(int mode, bool masks, bool stats) {
-#define OCC(A, M, S) if (mode == A && masks == M && stats == S) return occupancy<A, M, S>();
+int imba_trace_blocks_per_sm(int mode, bool masks, bool stats, bool flat) {
+#define OCC(A, M, S) if (mode == A && masks == M && stats == S) return occupancy<A, M, S>(flat);
     FOR_ALL_VARIANTS(OCC)
 #undef OCC
     return 0;

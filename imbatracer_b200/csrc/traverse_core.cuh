@@ -52,15 +52,46 @@ __device__ __forceinline__ bool mask_opaque(const TraceArgs& P, int tri_id, floa
 
 struct HitRegs { float tbest, ubest; int tri_best, inst_best; };
 
+/* Byte j of x as 1 + byte * 2^-15: ONE permute on the ALU pipe instead of an I2F on the XU pipe (the busiest pipe of the
+ * traversal kernel, profiles/r1f_trace_full.csv).  The slab test then runs as fma(1 + q 2^-15, adj 2^15, org - adj 2^15): one
+ * extra rounding of 2^-9 cell per node axis, far inside the 1/64 cell of slack the builder leaves (bvh8.h). */
+#ifndef IMBA_PRMT_AXES
+#define IMBA_PRMT_AXES 0   /* bit a set: axis a converts by permute (tuning switch) */
+#endif
+template <int J> __device__ __forceinline__ float byte_m(uint32_t x) { return __uint_as_float(__byte_perm(x, 0x3F800000u, 0x7604u | (J << 4))); }
+template <int AXIS, int J> __device__ __forceinline__ float byte_cvt(uint32_t x) {
+    if ((IMBA_PRMT_AXES >> AXIS) & 1) return byte_m<J>(x);
+    return (float)((x >> (8 * J)) & 0xffu);
+}
+template <int AXIS> __device__ __forceinline__ void slab_setup(float& adj, float& org) {
+    if ((IMBA_PRMT_AXES >> AXIS) & 1) { adj *= 32768.0f; org = org - adj; }
+}
+
+template <int J>
+__device__ __forceinline__ uint32_t child_test(uint32_t nx, uint32_t fx, uint32_t ny, uint32_t fy, uint32_t nz, uint32_t fz, float adjx, float adjy, float adjz,
+                                               float orgx, float orgy, float orgz, float tmin, float tbest, uint32_t child_bits4, uint32_t bit_index4) {
+    const float t0x = __fmaf_rn(byte_cvt<0, J>(nx), adjx, orgx), t1x = __fmaf_rn(byte_cvt<0, J>(fx), adjx, orgx);
+    const float t0y = __fmaf_rn(byte_cvt<1, J>(ny), adjy, orgy), t1y = __fmaf_rn(byte_cvt<1, J>(fy), adjy, orgy);
+    const float t0z = __fmaf_rn(byte_cvt<2, J>(nz), adjz, orgz), t1z = __fmaf_rn(byte_cvt<2, J>(fz), adjz, orgz);
+    const float tn = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, tmin));
+    const float tf = fminf(fminf(t1x, t1y), fminf(t1z, tbest));
+    if (tn <= tf * IMBA_ROBUST_TFAR) {
+        const uint32_t cb = (child_bits4 >> (8 * J)) & 0xffu, bi = (bit_index4 >> (8 * J)) & 0xffu;
+        return cb << bi;
+    }
+    return 0u;
+}
+
 /* Intersects the 8 quantised child boxes of one node: returns the 8-bit inner / 24-bit primitive hit mask. */
 __device__ __forceinline__ uint32_t node_step(const uint4 n0, const uint4 n1, const uint4 n2, const uint4 n3, const uint4 n4, const RayRegs& r, float tmin, float tbest) {
     const uint32_t e_imask = n0.w;
-    const float adjx = __uint_as_float((e_imask & 0xffu) << 23) * r.ix;
-    const float adjy = __uint_as_float(((e_imask >> 8) & 0xffu) << 23) * r.iy;
-    const float adjz = __uint_as_float(((e_imask >> 16) & 0xffu) << 23) * r.iz;
-    const float orgx = (__uint_as_float(n0.x) - r.ox) * r.ix;
-    const float orgy = (__uint_as_float(n0.y) - r.oy) * r.iy;
-    const float orgz = (__uint_as_float(n0.z) - r.oz) * r.iz;
+    float adjx = __uint_as_float((e_imask & 0xffu) << 23) * r.ix;
+    float adjy = __uint_as_float(((e_imask >> 8) & 0xffu) << 23) * r.iy;
+    float adjz = __uint_as_float(((e_imask >> 16) & 0xffu) << 23) * r.iz;
+    float orgx = (__uint_as_float(n0.x) - r.ox) * r.ix;
+    float orgy = (__uint_as_float(n0.y) - r.oy) * r.iy;
+    float orgz = (__uint_as_float(n0.z) - r.oz) * r.iz;
+    slab_setup<0>(adjx, orgx); slab_setup<1>(adjy, orgy); slab_setup<2>(adjz, orgz);
     uint32_t hitmask = 0;
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
@@ -74,18 +105,10 @@ __device__ __forceinline__ uint32_t node_step(const uint4 n0, const uint4 n1, co
         const uint32_t nx = r.ix < 0.0f ? qhix : qlox, fx = r.ix < 0.0f ? qlox : qhix;
         const uint32_t ny = r.iy < 0.0f ? qhiy : qloy, fy = r.iy < 0.0f ? qloy : qhiy;
         const uint32_t nz = r.iz < 0.0f ? qhiz : qloz, fz = r.iz < 0.0f ? qloz : qhiz;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const float t0x = __fmaf_rn(byte_f(nx, j), adjx, orgx), t1x = __fmaf_rn(byte_f(fx, j), adjx, orgx);
-            const float t0y = __fmaf_rn(byte_f(ny, j), adjy, orgy), t1y = __fmaf_rn(byte_f(fy, j), adjy, orgy);
-            const float t0z = __fmaf_rn(byte_f(nz, j), adjz, orgz), t1z = __fmaf_rn(byte_f(fz, j), adjz, orgz);
-            const float tn = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, tmin));
-            const float tf = fminf(fminf(t1x, t1y), fminf(t1z, tbest));
-            if (tn <= tf * IMBA_ROBUST_TFAR) {
-                const uint32_t cb = (child_bits4 >> (8 * j)) & 0xffu, bi = (bit_index4 >> (8 * j)) & 0xffu;
-                hitmask |= cb << bi;
-            }
-        }
+        hitmask |= child_test<0>(nx, fx, ny, fy, nz, fz, adjx, adjy, adjz, orgx, orgy, orgz, tmin, tbest, child_bits4, bit_index4);
+        hitmask |= child_test<1>(nx, fx, ny, fy, nz, fz, adjx, adjy, adjz, orgx, orgy, orgz, tmin, tbest, child_bits4, bit_index4);
+        hitmask |= child_test<2>(nx, fx, ny, fy, nz, fz, adjx, adjy, adjz, orgx, orgy, orgz, tmin, tbest, child_bits4, bit_index4);
+        hitmask |= child_test<3>(nx, fx, ny, fy, nz, fz, adjx, adjy, adjz, orgx, orgy, orgz, tmin, tbest, child_bits4, bit_index4);
     }
     return hitmask;
 }
