@@ -29,6 +29,7 @@ from tests import refapi, raygen  # noqa: E402
 
 SCENES = ["cornell_org", "cornell_indirect", "cornell_water", "cornell_instances", "cornell_specular_front", "stilllife_proxy"]
 IMAGES = ["cornell_org", "cornell_indirect", "cornell_specular", "cornell_specular_front", "cornell_water"]
+RENDER_ONLY = ["cornell_specular"]   # scene arrays only (GPU layout): rendered against its golden image, no hit fixtures
 
 
 def main():
@@ -59,6 +60,10 @@ def main():
 
     if only:
         return
+    for name in RENDER_ONLY:
+        rs = refapi.RefScene(refapi.scene_path(name), True)
+        rs.flat(name).save(os.path.join(HERE, f"scene_{name}_gpu.npz"))
+        rs.close()
     # .bvh caches the reference's loader wrote next to the meshes while loading (render/scene.cpp:67, loaders/load_bvh.cpp)
     import shutil
     for f in ("CornellBox-Original.bvh", "CornellBox-Specular.bvh"):

@@ -1,0 +1,172 @@
+"""Parity ON THE CONFIGURATION bench.py MEASURES (BASELINE.json configs[1], configs[4]) and on the scenes whose structure is
+larger than L2: every ray of the four 4 Mi-ray bench batches on the full-detail stilllife-proxy (1.52 M triangles) against the
+CPU oracle, 64 Ki random rays on the 2 744-instance scene and on the 4.7 M-triangle terrain, and one VCM light + camera stage
+comparison with the reference's own VCMIntegrator on a 2 744-instance scene loaded by the reference's loader.
+
+Bar (ray_queue.h:254-265, integrator.h:57): closest hit bit-exact (tri_id, inst_id, t, u), occlusion flag-equal, outside the
+two documented degenerate classes of DESIGN.md section 1 -- whose SIZE is asserted as a count:
+  (1) 0-distance ties: rays with tmin = 0 that start on geometry (none in the bench batches: tmin = 1e-3 t);
+  (2) coplanar hit-or-miss: rays inside the plane of a triangle, det = n.d at rounding level."""
+import os
+
+import numpy as np
+import pytest
+
+from imbatracer_b200 import abi
+from tests import refapi
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def bench_setup():
+    import torch
+    import bench
+    from imbatracer_b200 import api
+    assert torch.cuda.is_available()
+    torch.cuda.set_device(0)
+    flat = bench.load_flat()
+    scene = api.Scene(flat)
+    batches = bench.make_batches(flat, bench.RAYS_PER_BATCH, 0x1234ABCD, scene=scene)
+    yield flat, scene, batches
+    scene.close()
+
+
+def coplanar(flat, rays, hits):
+    """True where the ray lies in the plane of the triangle `hits` reports: |n.d| < 1e-6 |n||d| (single-mesh scenes)."""
+    idx = flat.indices.reshape(-1, 4); v = flat.vertices.reshape(-1, 4)[:, :3].astype(np.float64)
+    p0, p1, p2 = (v[idx[hits["tri_id"], k]] for k in range(3))
+    n = np.cross(p0 - p1, p2 - p0); d = rays["dir"].astype(np.float64)
+    return np.abs((n * d).sum(1)) < 1e-6 * np.linalg.norm(n, axis=1) * np.linalg.norm(d, axis=1)
+
+
+# number of rays of each 4 Mi-ray bench batch (seed 0x1234ABCD) that fall into the coplanar class; everything else is exact
+COPLANAR_COUNT = {"coherent_closest": 0, "incoherent_closest": 0, "coherent_occluded": 0, "incoherent_occluded": 4}
+
+
+@pytest.mark.parametrize("name,any_hit", [("coherent_closest", 0), ("incoherent_closest", 0), ("coherent_occluded", 1), ("incoherent_occluded", 1)])
+def test_every_ray_of_the_bench_batches_matches_the_oracle(bench_setup, name, any_hit):
+    import torch
+    from imbatracer_b200 import api
+    flat, scene, batches = bench_setup
+    rays = batches[name]
+    assert len(rays) == 1 << 22
+    got = api.hits_from_device(scene.trace(api.rays_to_device(rays), any_hit=bool(any_hit)))
+    torch.cuda.synchronize()
+    want = refapi.trace_oracle(flat, rays, any_hit=bool(any_hit))
+    assert not ((rays["tmin"] == 0) & (got["tri_id"] >= 0) & (got["tmax"] == 0)).any()     # class (1) does not occur here
+    if any_hit:
+        differ = (got["tri_id"] >= 0) != (want["tri_id"] >= 0)
+    else:
+        differ = (got.view(np.uint8).reshape(-1, 16) != want.view(np.uint8).reshape(-1, 16)).any(1)
+    bad = np.nonzero(differ)[0]
+    assert len(bad) == COPLANAR_COUNT[name], (name, len(bad), rays[bad[:4]], got[bad[:4]], want[bad[:4]])
+    if len(bad):
+        # class (2): the CUDA path (wider quantised boxes) reaches a triangle the ray is coplanar with, the oracle does not
+        assert (want["tri_id"][bad] < 0).all() and (got["tri_id"][bad] >= 0).all()
+        closest = api.hits_from_device(scene.trace(api.rays_to_device(np.ascontiguousarray(rays[bad]))))
+        assert coplanar(flat, rays[bad], closest).all()
+
+
+def test_bench_closest_and_occluded_batches_are_consistent(bench_setup):
+    """Size-independent property at full size: a shadow ray is occluded iff the closest-hit kernel finds a hit inside its
+    (tmin, tmax) interval -- the two kernels share the triangle test, so the flags must agree on every one of the 4 Mi rays."""
+    import torch
+    from imbatracer_b200 import api
+    flat, scene, batches = bench_setup
+    for name in ("coherent_occluded", "incoherent_occluded"):
+        d = api.rays_to_device(batches[name])
+        occ = scene.trace(d, any_hit=True).clone(); closest = scene.trace(d)
+        torch.cuda.synchronize()
+        assert torch.equal(occ[:, 0] >= 0, closest[:, 0] >= 0), name
+
+
+@pytest.mark.parametrize("which", ["instanced_2744", "terrain_4.7M"])
+def test_large_scenes_match_oracle(which):
+    """configs[4]-sized structures: 2 744 rigid instances of Cornell-water (19.4 M instanced triangles, two-level traversal) and a
+    4.7 M-triangle terrain (264 MB of nodes + triangles, larger than L2), 64 Ki random rays each, closest hit and occlusion."""
+    import torch
+    import bench
+    from imbatracer_b200 import api, procedural
+    from tests import raygen
+    from tests.conftest import zero_distance_ties
+    flat = procedural.instanced_grid(bench.load_cornell("cornell_water"), 14, 14, 14) if which == "instanced_2744" else procedural.terrain(1536)
+    scene = api.Scene(flat)
+    try:
+        if which == "instanced_2744":
+            assert len(flat.instances) == 2744
+        else:
+            assert flat.tri_count == 4718594 and scene.stats()["bytes"] > 126e6
+        rays = raygen.random_rays(flat, 1 << 16, 23)
+        got = api.hits_from_device(scene.trace(api.rays_to_device(rays)))
+        occ = api.hits_from_device(scene.trace(api.rays_to_device(rays), any_hit=True))
+        torch.cuda.synchronize()
+        want = refapi.trace_oracle(flat, rays)
+        want_occ = refapi.trace_oracle(flat, rays, any_hit=True)
+        ties = zero_distance_ties(rays, got, want, occ, want_occ)
+        assert ties.sum() == 0
+        assert got.tobytes() == want.tobytes()
+        assert np.array_equal(occ["tri_id"] >= 0, want_occ["tri_id"] >= 0)
+        hit = got["tri_id"] >= 0
+        assert 0.2 < hit.mean() < 1.0
+        if which == "instanced_2744":
+            assert len(np.unique(got["inst_id"][hit])) > 1000      # the rays do reach most of the instances
+    finally:
+        scene.close()
+
+
+GRID_SCENE = "cornell_grid14"
+
+
+def write_grid_scene(n=14, spacing=3.0, seed=0x5EED):
+    """n^3 instances of CornellBox-Water.obj on a jittered grid, as a .scene file (grammar: build_scene.cpp:451-503) next to the
+    scratch copy of the reference's Cornell scenes; the reference's loader + SBVH builder + top-level builder then build it."""
+    path = os.path.join(refapi.REF_SCENES, "cornell", GRID_SCENE + ".scene")
+    rng = np.random.default_rng(seed)
+    ext = (n - 1) * spacing
+    lines = [f"pos {ext / 2:.6f} {ext / 2 + 0.1 * ext:.6f} {ext + 0.6 * ext + 3.0:.6f}", "dir 0 -0.05 -1", "up 0 1 0", "",
+             "mesh CornellBox-Water.obj", "accel CornellBox-Water.bvh", ""]
+    for ix in range(n):
+        for iy in range(n):
+            for iz in range(n):
+                p = (np.array([ix, iy, iz]) + (rng.random(3) - 0.5) * 0.3) * spacing
+                s = 0.8 + 0.4 * rng.random()
+                lines += ["instance 0", f"pos {p[0]:.6f} {p[1]:.6f} {p[2]:.6f}", f"scale {s:.6f} {s:.6f} {s:.6f}", f"rot 0 {360 * rng.random():.4f} 0", ""]
+    text = "\n".join(lines) + "\n"
+    if not os.path.exists(path) or open(path).read() != text:
+        with open(path, "w") as f:
+            f.write(text)
+    return path
+
+
+@pytest.mark.skipif(not refapi.have_ref() or not os.path.isdir(refapi.REF_SCENES), reason="oracle/_ref not built")
+def test_vcm_stages_on_the_2744_instance_scene_match_reference():
+    """One VCM light + camera stage comparison (tests/vcm_harness.py) at the instance count the bench uses for configs[4]: the
+    reference's own loader, top-level builder and VCMIntegrator<VCM>::process_light_rays / process_camera_rays against the CUDA
+    stages on identical wavefronts; merging and connections go through the reference's light-vertex cache on both sides."""
+    from tests import vcm_harness as vh
+    write_grid_scene()
+    res = vh.run(GRID_SCENE, "vcm", w=64, h=64, waves=3, from_reference=True)
+    assert len(res["light"]) >= 2 and len(res["camera"]) >= 2
+    for r in res["light"]:
+        c = r["cont"]
+        assert c["ref"] == c["dev"] and c["only_one_side"] == 0, r
+        if c["ref"]:
+            assert c["same_order"] and c["rng_equal"] == 1.0 and c["len_equal"] == 1.0 and c["close"] >= 0.999, r
+        for part in ("connect", "cache"):
+            p = r[part]
+            assert p["ref"] == p["dev"] and p["only_one_side"] <= 0.002 * max(p["ref"], 1), r
+            if p["ref"]:
+                assert p["close"] >= 0.998, r
+    assert res["light"][0]["cache"]["ref"] > 0
+    for r in res["camera"]:
+        c = r["cont"]
+        assert c["ref"] == c["dev"] and c["only_one_side"] == 0, r
+        if c["ref"]:
+            assert c["same_order"] and c["rng_equal"] == 1.0 and c["len_equal"] == 1.0 and c["close"] >= 0.999, r
+        p = r["shadow"]
+        assert p["ref"] == p["dev"] and p["only_one_side"] <= 0.002 * max(p["ref"], 1), r
+        if p["ref"]:
+            assert p["close"] >= 0.998, r
+        assert r["fb_rel_err"] < 2e-3, r

@@ -97,15 +97,19 @@ def test_rng_known_answers():
 
 
 @pytest.mark.skipif(not refapi.have_ref() or not os.path.isdir(refapi.REF_SCENES), reason="reference build not present")
-@pytest.mark.parametrize("scene,algo,image,tol", [("cornell_org", 0, "cornell_org", 0.06), ("cornell_indirect", 1, "cornell_indirect", 0.08)])
-def test_reference_pipeline_with_oracle_reproduces_golden_image(scene, algo, image, tol):
-    """The reference's own integrators (PT / BPT) running on the oracle's traversal must converge to the reference's
-    golden PNG (test/render_refs.sh settings, 128x128, gamma-0.5 RMSE as test/run_bench.py:113-129 measures it)."""
+@pytest.mark.parametrize("scene,algo,radius,iters,tol", [("cornell_org", 0, 2.0, 48, 0.04), ("cornell_indirect", 1, 2.0, 48, 0.03), ("cornell_specular", 2, 0.003, 64, 0.08),
+                                                        ("cornell_specular_front", 2, 0.003, 64, 0.07), ("cornell_water", 2, 0.003, 64, 0.11)])
+def test_reference_pipeline_with_oracle_reproduces_golden_image(scene, algo, radius, iters, tol):
+    """The reference's own integrators running on the oracle's traversal must converge to all five usable golden PNGs of the
+    reference with the integrator and radius test/render_refs.sh:10-23 used for each (PT, BPT, VCM -r 0.003), at 128x128,
+    gamma-0.5 RMSE as test/run_bench.py:113-129 measures it.  Tolerances = what 48 / 64 samples per pixel leave at this size
+    (0.025 / 0.017 / 0.061 / 0.051 / 0.090 measured); the three VCM scenes keep a bias of ~0.05 at 128^2 because the golden PNGs
+    clamp their caustics per 1024^2 pixel (the device renders are gated at 1024^2 and 0.03, tests/test_goldens_gpu.py)."""
     rs = refapi.RefScene(refapi.scene_path(scene), False)
-    img, st = rs.render(algo, 128, 128, iterations=48)
+    img, st = rs.render(algo, 128, 128, iterations=iters, radius_factor=radius, tile=64)
     rs.close()
-    got = np.clip(img / 48.0, 0, None) ** 0.5
-    want = np.load(os.path.join(GOLDEN, f"ref_{image}_128.npy")) ** 0.5
+    got = np.clip(img / float(iters), 0, None) ** 0.5
+    want = np.load(os.path.join(GOLDEN, f"ref_{scene}_128.npy")) ** 0.5
     rmse = float(np.sqrt(np.mean((np.clip(got, 0, 1) - np.clip(want, 0, 1)) ** 2)))
     assert rmse < tol, rmse
 
