@@ -117,6 +117,10 @@ extern "C" int imba_integrator_preprocess(imba_integrator* it) {
     if (!it) { imba_set_error("null argument"); return IMBA_ERR_INVALID; }
     const int quads = ((it->cam.width + 7) / 8) * ((it->cam.height + 7) / 8);
     const int n = std::min(quads * 4, it->capacity / 4 * 4); // capacity >= width * height >= 4 * quads
+    if (n <= 0) {   // fewer than four samples in the whole image: nothing to probe with (integrator.cpp:68-70 leaves the size at 1)
+        it->pixel_size = 1.0f;
+        return it->cfg.algorithm != IMBA_ALGO_PT ? imba_vcm_preprocess(it) : IMBA_OK;
+    }
     IMBA_CUDA(cudaMemsetAsync(it->d_probe, 0, 16, it->stream), IMBA_ERR_CUDA);
     IMBA_CUDA(imba_probe_raygen(it->cam, it->rays[0], n, it->stream), IMBA_ERR_CUDA);
     int rc = imba_scene_trace(it->scene, (const imba_ray*)it->rays[0], (imba_hit*)it->hits, n, 0, nullptr, it->stream);
@@ -133,6 +137,22 @@ extern "C" int imba_integrator_preprocess(imba_integrator* it) {
 
 extern "C" float imba_integrator_pixel_size(const imba_integrator* it) { return it ? it->pixel_size : 0.0f; }
 extern "C" int imba_integrator_reset(imba_integrator* it) { if (!it) return IMBA_ERR_INVALID; it->iteration = 0; return IMBA_OK; }
+
+/* Camera moved (CameraControl -> PerspectiveCamera::move, camera.h:27-50; the reference then calls Integrator::reset,
+ * render_window.cpp:97-101): new position / direction / up, restart of the progressive schedule.  Waits for pending work;
+ * captured launch graphs hold the old camera by value and are dropped. */
+extern "C" int imba_integrator_set_camera(imba_integrator* it, const float pos[3], const float dir[3], const float up[3]) {
+    if (!it || !pos || !dir || !up) { imba_set_error("null argument"); return IMBA_ERR_INVALID; }
+    int rc = imba_integrator_sync(it);
+    if (rc != IMBA_OK) return rc;
+    for (int k = 0; k < 3; ++k) { it->cfg.cam_pos[k] = pos[k]; it->cfg.cam_dir[k] = dir[k]; it->cfg.cam_up[k] = up[k]; }
+    it->cam = make_camera(it->cfg);
+    if (it->tail_graph) { cudaGraphExecDestroy(it->tail_graph); it->tail_graph = nullptr; }
+    for (int i = 0; i < imba_integrator::kParkedGraphs; ++i)
+        if (it->parked_graph[i]) { cudaGraphExecDestroy(it->parked_graph[i]); it->parked_graph[i] = nullptr; it->parked_fb[i] = nullptr; }
+    it->iteration = 0;
+    return IMBA_OK;
+}
 
 static int pt_wavefront(imba_integrator* it, int cur, int capacity) {
     const DeviceShading& S = *imba_shading_view(it->scene);

@@ -44,6 +44,16 @@ struct PixelAliveKey {    // standalone compact_rays (no hit array): keep states
     }
 };
 
+struct ArrayKey {         // sort_by_material with the keys computed by the caller (the reference's GetMatIDFn runs on the host)
+    const int* keys_in; int nbins;
+    __device__ __forceinline__ int operator()(int i) const { const int k = __ldg(keys_in + i); return k < 0 ? 0 : (k >= nbins ? nbins - 1 : k); }
+};
+
+struct HitKey {           // compact_hits alone: hits first
+    const int4* hits;
+    __device__ __forceinline__ int operator()(int i) const { return __ldg(&hits[i].x) >= 0 ? 0 : 1; }
+};
+
 template <class KeyFn>
 __global__ void __launch_bounds__(PART_THREADS) part_hist(KeyFn key, const int* count_ptr, int count_imm, int nbins, int* keys, int* block_hist) {
     extern __shared__ int sh[];
@@ -224,4 +234,94 @@ cudaError_t imba_gather_queue(const int* idx, const int* n_ptr, int n_imm, int c
     if (capacity <= 0) return cudaSuccess;
     gather_queue<<<(capacity + 255) / 256, 256, 0, st>>>(rays, hits, (const char*)states, state_bytes, idx, n_ptr, n_imm, rays_out, hits_out, (char*)states_out);
     return cudaGetLastError();
+}
+
+
+/* ---- the same primitives on HOST arrays: RayQueue::{compact_hits, compact_rays, sort_by_material} keep their queues in host
+ * memory (ray_queue.h:161-244); these entry points stage the arrays through device memory, run the kernels above and copy the
+ * result back in place.  Used by the C++ mirror of RayQueue (include/imba_b200.hpp); the device integrators never come here. */
+#include "api_common.h"
+
+namespace {
+struct DeviceBuf {
+    void* p = nullptr;
+    ~DeviceBuf() { cudaFree(p); }
+    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 16); }
+};
+}
+
+extern "C" int imba_queue_compact_hits_host(imba_ray* h_rays, imba_hit* h_hits, void* h_states, int state_bytes, int count, int* hit_count) {
+    if (count < 0 || state_bytes < 8 || state_bytes % 8 || !hit_count || (count > 0 && (!h_rays || !h_hits || !h_states))) { imba_set_error("invalid argument"); return IMBA_ERR_INVALID; }
+    *hit_count = 0;
+    if (count == 0) return IMBA_OK;
+    int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) { imba_set_error("no CUDA device (this library has no CPU path)"); return IMBA_ERR_NO_DEVICE; }
+    DeviceBuf rays, hits, states, rays_o, hits_o, states_o;
+    const size_t rb = (size_t)count * 32, hb = (size_t)count * 16, sb = (size_t)count * state_bytes;
+    IMBA_CUDA(rays.alloc(rb), IMBA_ERR_CUDA); IMBA_CUDA(hits.alloc(hb), IMBA_ERR_CUDA); IMBA_CUDA(states.alloc(sb), IMBA_ERR_CUDA);
+    IMBA_CUDA(rays_o.alloc(rb), IMBA_ERR_CUDA); IMBA_CUDA(hits_o.alloc(hb), IMBA_ERR_CUDA); IMBA_CUDA(states_o.alloc(sb), IMBA_ERR_CUDA);
+    cudaStream_t st = cudaStreamPerThread;
+    IMBA_CUDA(cudaMemcpyAsync(rays.p, h_rays, rb, cudaMemcpyHostToDevice, st), IMBA_ERR_CUDA);
+    IMBA_CUDA(cudaMemcpyAsync(hits.p, h_hits, hb, cudaMemcpyHostToDevice, st), IMBA_ERR_CUDA);
+    IMBA_CUDA(cudaMemcpyAsync(states.p, h_states, sb, cudaMemcpyHostToDevice, st), IMBA_ERR_CUDA);
+    PartitionBuffers b;
+    IMBA_CUDA(imba_partition_alloc(b, count, 2), IMBA_ERR_CUDA);
+    cudaError_t e = run_partition(b, HitKey{ (const int4*)hits.p }, nullptr, count, count, 2, st);
+    if (e == cudaSuccess) e = imba_gather_queue(b.indices, nullptr, count, count, (const float4*)rays.p, (const int4*)hits.p, states.p, state_bytes,
+                                                (float4*)rays_o.p, (int4*)hits_o.p, states_o.p, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(hit_count, b.bin_start + 1, sizeof(int), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h_rays, rays_o.p, rb, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h_hits, hits_o.p, hb, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h_states, states_o.p, sb, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    imba_partition_free(b);
+    g_imba_launches.fetch_add(4);
+    IMBA_CUDA(e, IMBA_ERR_CUDA);
+    return IMBA_OK;
+}
+
+extern "C" int imba_queue_compact_rays_host(imba_ray* h_rays, void* h_states, int state_bytes, int count, int* kept) {
+    if (count < 0 || state_bytes < 8 || state_bytes % 8 || !kept || (count > 0 && (!h_rays || !h_states))) { imba_set_error("invalid argument"); return IMBA_ERR_INVALID; }
+    *kept = 0;
+    if (count == 0) return IMBA_OK;
+    int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) { imba_set_error("no CUDA device (this library has no CPU path)"); return IMBA_ERR_NO_DEVICE; }
+    DeviceBuf rays, states, rays_o, states_o, cnt;
+    const size_t rb = (size_t)count * 32, sb = (size_t)count * state_bytes;
+    IMBA_CUDA(rays.alloc(rb), IMBA_ERR_CUDA); IMBA_CUDA(states.alloc(sb), IMBA_ERR_CUDA); IMBA_CUDA(rays_o.alloc(rb), IMBA_ERR_CUDA);
+    IMBA_CUDA(states_o.alloc(sb), IMBA_ERR_CUDA); IMBA_CUDA(cnt.alloc(sizeof(int)), IMBA_ERR_CUDA);
+    cudaStream_t st = cudaStreamPerThread;
+    IMBA_CUDA(cudaMemcpyAsync(rays.p, h_rays, rb, cudaMemcpyHostToDevice, st), IMBA_ERR_CUDA);
+    IMBA_CUDA(cudaMemcpyAsync(states.p, h_states, sb, cudaMemcpyHostToDevice, st), IMBA_ERR_CUDA);
+    PartitionBuffers b;
+    IMBA_CUDA(imba_partition_alloc(b, count, 2), IMBA_ERR_CUDA);
+    cudaError_t e = imba_compact_alive(b, nullptr, (const float4*)rays.p, states.p, state_bytes, nullptr, count, count, (float4*)rays_o.p, states_o.p, (int*)cnt.p, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(kept, cnt.p, sizeof(int), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e == cudaSuccess && *kept > 0) {
+        e = cudaMemcpyAsync(h_rays, rays_o.p, (size_t)*kept * 32, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(h_states, states_o.p, (size_t)*kept * state_bytes, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    }
+    imba_partition_free(b);
+    g_imba_launches.fetch_add(4);
+    IMBA_CUDA(e, IMBA_ERR_CUDA);
+    return IMBA_OK;
+}
+
+extern "C" int imba_queue_sort_keys_host(const int* h_keys, int count, int num_bins, int* h_sorted_indices) {
+    if (count < 0 || num_bins <= 0 || (count > 0 && (!h_keys || !h_sorted_indices))) { imba_set_error("invalid argument"); return IMBA_ERR_INVALID; }
+    if (count == 0) return IMBA_OK;
+    int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) { imba_set_error("no CUDA device (this library has no CPU path)"); return IMBA_ERR_NO_DEVICE; }
+    DeviceBuf keys;
+    IMBA_CUDA(keys.alloc((size_t)count * sizeof(int)), IMBA_ERR_CUDA);
+    cudaStream_t st = cudaStreamPerThread;
+    IMBA_CUDA(cudaMemcpyAsync(keys.p, h_keys, (size_t)count * sizeof(int), cudaMemcpyHostToDevice, st), IMBA_ERR_CUDA);
+    PartitionBuffers b;
+    IMBA_CUDA(imba_partition_alloc(b, count, num_bins), IMBA_ERR_CUDA);
+    cudaError_t e = run_partition(b, ArrayKey{ (const int*)keys.p, num_bins }, nullptr, count, count, num_bins, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h_sorted_indices, b.indices, (size_t)count * sizeof(int), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    imba_partition_free(b);
+    g_imba_launches.fetch_add(3);
+    IMBA_CUDA(e, IMBA_ERR_CUDA);
+    return IMBA_OK;
 }

@@ -22,6 +22,20 @@ def accumulate_iteration(fb: torch.Tensor, total: torch.Tensor, group=None, stre
         fb.zero_()
 
 
+def agree_to_stop(local_stop: bool, group=None, device=None) -> bool:
+    """Collective stop decision for time-limited rendering (-t, render_window.cpp:71-74): every rank measures its own wall clock,
+    and every step of the render loop contains a framebuffer all-reduce -- so ranks must leave the loop after the SAME step or
+    the slower one waits for a collective nobody joins.  All ranks call this once per step; the loop stops as soon as any rank's
+    clock has run out (MAX over the flags)."""
+    if not (dist.is_initialized() and dist.get_world_size(group) > 1):
+        return bool(local_stop)
+    if device is None:
+        device = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
+    flag = torch.tensor([1 if local_stop else 0], dtype=torch.int32, device=device)
+    dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=group)
+    return bool(int(flag.item()))
+
+
 class _null:
     def __enter__(self):
         return self

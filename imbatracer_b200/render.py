@@ -61,7 +61,7 @@ def main(argv=None):
     import torch
     import torch.distributed as dist
     from . import api
-    from .distributed import ProgressiveRenderer
+    from .distributed import ProgressiveRenderer, agree_to_stop
     from .scene import FlatScene
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
@@ -91,7 +91,7 @@ def main(argv=None):
                     from PIL import Image
                     Image.fromarray(to_png_array(part, a.gamma)).save(f"{a.intermediate_path}{int(el * 1000)}ms.png")
                 next_dump += a.intermediate_time
-            if a.t > 0 and el >= a.t:
+            if a.t > 0 and agree_to_stop(el >= a.t):   # collective: all ranks leave after the same step
                 break
     img = loop.image().cpu().numpy()
     secs = time.time() - t0

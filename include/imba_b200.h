@@ -260,6 +260,15 @@ int imba_queue_sort_by_material(imba_scene* scene, const imba_hit* d_hits, int c
 /* compact_rays (ray_queue.h:188-207): stable removal of states whose pixel_id (first int) is < 0. */
 int imba_queue_compact_rays(const imba_ray* d_rays, const void* d_states, int state_bytes, imba_ray* d_rays_out,
                             void* d_states_out, int count, int* d_out_count, void* stream);
+/* The same three primitives for queues kept in HOST memory, as RayQueue keeps them (ray_queue.h:161-244): the arrays are staged
+ * through device memory, partitioned by the kernels above and copied back IN PLACE.  compact_hits: hits first, both parts in
+ * their original order (the reference's swap loop keeps only the hits in order; callers drop the misses right after,
+ * pt.cpp:119).  compact_rays: states whose pixel_id (first int) is < 0 are removed, *kept = new size.  sort_keys: counting sort
+ * of the element indices 0..count-1 by h_keys[i] in [0, num_bins) -- the keys are what the caller's GetMatIDFn returned
+ * (ray_queue.h:209-244) -- stable inside a bin. */
+int imba_queue_compact_hits_host(imba_ray* h_rays, imba_hit* h_hits, void* h_states, int state_bytes, int count, int* hit_count);
+int imba_queue_compact_rays_host(imba_ray* h_rays, void* h_states, int state_bytes, int count, int* kept);
+int imba_queue_sort_keys_host(const int* h_keys, int count, int num_bins, int* h_sorted_indices);
 
 /* ------------------------------------------------------------------------------------------
  * L2: integrators (render/integrators/{pt,vcm}.*) behind Integrator::{render,reset,preprocess,pixel_size}
@@ -299,6 +308,9 @@ int   imba_integrator_preprocess(imba_integrator* it);
 float imba_integrator_pixel_size(const imba_integrator* it);
 /* Integrator::reset (vcm.h:69-72). */
 int   imba_integrator_reset(imba_integrator* it);
+/* Camera moved (PerspectiveCamera::move, camera.h:27-50, followed by Integrator::reset as render_window.cpp:97-101 does):
+ * waits for pending work, installs the new position / direction / up and restarts the progressive schedule. */
+int   imba_integrator_set_camera(imba_integrator* it, const float pos[3], const float dir[3], const float up[3]);
 /* Integrator::render: runs `iterations` progressive iterations, ADDING un-normalised radiance into the
  * device accumulation buffer (the caller divides by iterations*spp, render_window.cpp:105,178). Asynchronous. */
 int   imba_integrator_render(imba_integrator* it, int iterations);

@@ -54,6 +54,11 @@
 
 #define IMBA_B200_NO_L1_DECLS /* the shim headers declare the same symbols inside namespaces */
 #include "../include/imba_b200.h"
+#ifdef IMBA_REF_ON_B200
+/* oracle/Makefile target ref_b200: this build links libimba_b200.so instead of the traversal restatement, keeps the scene's
+ * "gpu" arrays in device memory (oracle/shim_cuda) and also exercises the product's plug-ins for the reference's interfaces. */
+#include "../include/imba_b200_ref.hpp"
+#endif
 
 using namespace imba;
 
@@ -202,9 +207,24 @@ void ref_scene_camera(void* h, float* pos, float* dir, float* up) {
     for (int i = 0; i < 3; ++i) { pos[i] = rs->cam_pos[i]; dir[i] = rs->cam_dir[i]; up[i] = rs->cam_up[i]; }
 }
 
+/// Makes the reference's std::random_device reproducible (oracle/shim/det_random.h); 0 = the real device again.
+void ref_set_seed(uint64_t seed) { imba_det::seed(seed); }
+
+/// 1 when this library is the reference linked against libimba_b200.so (Makefile target ref_b200), 0 for the oracle build.
+int ref_is_linked_to_product(void) {
+#ifdef IMBA_REF_ON_B200
+    return 1;
+#else
+    return 0;
+#endif
+}
+
 /// Fills `d` with pointers into storage owned by the handle.
 int ref_scene_export(void* h, imba_scene_desc* d) {
     auto rs = (RefScene*)h;
+#ifdef IMBA_REF_ON_B200
+    if (rs->gpu_layout) return -4;   // the traversal arrays live in device memory in this build
+#endif
     Scene& sc = *rs->scene;
     memset(d, 0, sizeof(*d));
     rs->mesh_vertex_base.assign(1, 0); rs->mesh_tri_base.assign(1, 0);
@@ -391,6 +411,77 @@ int ref_render(void* h, int algo, int w, int hgt, float fov, int spp, int iterat
     if (pixel_size_out) *pixel_size_out = px;
     return 0;
 }
+
+#ifdef IMBA_REF_ON_B200
+/// The product's plug-ins at the reference's own interfaces (include/imba_b200_ref.hpp), driven like frontend/main.cpp:117-163 +
+/// render_window.cpp:93-95 drive the reference's classes.
+///   mode 0: the reference's PathTracer / VCMIntegrator<algo> on imba::B200WavefrontScheduler (a RayScheduler subclass);
+///   mode 1: imba::B200Integrator (an Integrator subclass, everything on the device) -- needs the host ("cpu") layout for the export.
+/// out_rgb: SUM over iterations; stats: primary / shadow rays; pixel_sizes[0] = Integrator::pixel_size() (the reference's probe through
+/// the linked traversal symbols), pixel_sizes[1] = the device integrator's own probe (mode 1).
+int ref_render_plugin(void* h, int mode, int algo, int w, int hgt, float fov, int spp, int iterations, int threads, int tile, int max_path_len,
+                      int light_paths, int connections, int knn, float radius_factor, unsigned seed, float* out_rgb, uint64_t* stats, float* pixel_sizes) {
+    Quiet q;
+    auto rs = (RefScene*)h;
+    Scene& scene = *rs->scene;
+    UserSettings s;
+    s.width = w; s.height = hgt; s.fov = fov; s.concurrent_spp = spp; s.thread_count = threads; s.tile_size = tile;
+    s.max_path_len = max_path_len; s.light_path_count = light_paths > 0 ? light_paths : w * hgt / 2;
+    s.num_connections = connections; s.num_knn = knn; s.radius_factor = radius_factor;
+    s.traversal_platform = rs->gpu_layout ? UserSettings::gpu : UserSettings::cpu;
+    s.algorithm = (UserSettings::Algorithm)algo;
+    const bool gpu = rs->gpu_layout;
+    PerspectiveCamera cam(s.width, s.height, s.fov);
+    setup_camera(cam, rs->cam_pos, rs->cam_dir, rs->cam_up);
+    AtomicImage img(w, hgt); img.clear();
+    pixel_sizes[0] = pixel_sizes[1] = 0.0f; stats[0] = stats[1] = 0;
+    try {
+        if (mode == 1) {
+            imba_scene_desc d;
+            const int rc = ref_scene_export(h, &d);
+            if (rc != 0) return rc;
+            imba_scene* dev = imba_scene_create(&d);
+            if (!dev) { fprintf(stderr, "ref_render_plugin: %s\n", imba_last_error()); return -5; }
+            {
+                B200Integrator integ(scene, cam, dev, b200_render_settings(s, rs->cam_pos, rs->cam_dir, rs->cam_up, seed));
+                Integrator& base = integ;            // from here on only the reference's interface is used
+                base.preprocess();
+                pixel_sizes[0] = base.pixel_size(); pixel_sizes[1] = integ.device_pixel_size();
+                for (int i = 0; i < iterations; ++i) base.render(img);
+                base.reset();                        // camera unchanged: restarts the schedule, must not disturb the image
+                integ.ray_counts(stats);
+            }
+            imba_scene_destroy(dev);
+        } else if (s.algorithm == UserSettings::PT) {
+            PixelRayGen<PTState> ray_gen(s.width, s.height, s.concurrent_spp);
+            B200WavefrontScheduler<PTState, ShadowState> scheduler(ray_gen, scene, 1, w * hgt * spp, gpu);
+            PathTracer integ(scene, cam, scheduler, s.max_path_len);
+            integ.preprocess(); pixel_sizes[0] = integ.pixel_size();
+            for (int i = 0; i < iterations; ++i) integ.render(img);
+            stats[0] = scheduler.total_prim_rays(); stats[1] = scheduler.total_shadow_rays();
+        } else {
+            PixelRayGen<VCMState> ray_gen(s.width, s.height, s.concurrent_spp);
+            B200WavefrontScheduler<VCMState, VCMShadowState> scheduler(ray_gen, scene, s.num_connections + 1, w * hgt * spp, gpu);
+            std::unique_ptr<Integrator> integ;
+            switch (s.algorithm) {
+                case UserSettings::BPT:    integ.reset(new BPT(scene, cam, scheduler, s)); break;
+                case UserSettings::PPM:    integ.reset(new PPM(scene, cam, scheduler, s)); break;
+                case UserSettings::LT:     integ.reset(new LT(scene, cam, scheduler, s)); break;
+                case UserSettings::VCM_PT: integ.reset(new VCM_PT(scene, cam, scheduler, s)); break;
+                default:                   integ.reset(new VCM(scene, cam, scheduler, s)); break;
+            }
+            integ->preprocess(); pixel_sizes[0] = integ->pixel_size();
+            for (int i = 0; i < iterations; ++i) integ->render(img);
+            stats[0] = scheduler.total_prim_rays(); stats[1] = scheduler.total_shadow_rays();   // camera pass only (the light pass has its own TileScheduler)
+        }
+    } catch (const std::exception& e) {
+        fprintf(stderr, "ref_render_plugin: %s\n", e.what());
+        return -6;
+    }
+    for (int i = 0; i < w * hgt; ++i) { out_rgb[3 * i] = img.pixels()[i][0]; out_rgb[3 * i + 1] = img.pixels()[i][1]; out_rgb[3 * i + 2] = img.pixels()[i][2]; }
+    return 0;
+}
+#endif
 
 /// Camera rays exactly as PathTracer::render's sample function makes them (pt.cpp:168-177) for pixel
 /// centres + given jitter; rays[i] for pixel (x = i % w, y = i / w).

@@ -13,6 +13,7 @@ from imbatracer_b200.scene import FlatScene, from_desc
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORACLE_SO = os.path.join(ROOT, "oracle", "liboracle.so")
 REF_SO = os.path.join(ROOT, "oracle", "_ref", "libimba_ref.so")
+REF_B200_SO = os.path.join(ROOT, "oracle", "_ref", "libimba_ref_b200.so")   # the same reference sources linked against the product library
 REF_SCENES = os.path.join(ROOT, "oracle", "_ref", "scenes")  # scratch COPY of the reference's test/scenes (git-ignored)
 
 _oracle = None
@@ -45,6 +46,30 @@ def have_ref():
     return os.path.exists(REF_SO)
 
 
+def have_ref_b200():
+    return os.path.exists(REF_B200_SO)
+
+
+_ref_b200 = None
+
+
+def ref_b200():
+    """oracle/_ref/libimba_ref_b200.so (oracle/Makefile: ref_b200): the unmodified reference whose traversal symbols resolve to
+    imbatracer_b200/libimba_b200.so and whose AnyDSL arrays live in CUDA memory.  Needs a GPU."""
+    global _ref_b200
+    if _ref_b200 is None:
+        L = C.CDLL(REF_B200_SO)
+        vp, i32, f32 = C.c_void_p, C.c_int32, C.c_float
+        L.ref_scene_load.restype = vp; L.ref_scene_load.argtypes = [C.c_char_p, i32]
+        L.ref_scene_free.restype = None; L.ref_scene_free.argtypes = [vp]
+        L.ref_render.argtypes = [vp, i32, i32, i32, f32] + [i32] * 8 + [f32, vp, vp, vp, vp]
+        L.ref_set_seed.restype = None; L.ref_set_seed.argtypes = [C.c_uint64]
+        L.ref_render_plugin.argtypes = [vp, i32, i32, i32, i32, f32] + [i32] * 9 + [f32, C.c_uint32, vp, vp, vp]
+        assert L.ref_is_linked_to_product() == 1
+        _ref_b200 = L
+    return _ref_b200
+
+
 def ref():
     global _ref
     if _ref is None:
@@ -65,6 +90,7 @@ def ref():
         L.ref_vcm_camera_start.argtypes = [vp, i32, i32, f32, i32, i32, vp, vp, vp, vp]
         L.ref_scene_add_test_textures.argtypes = [vp, C.c_uint64]
         L.ref_scene_add_test_envmap.argtypes = [vp, C.c_uint64, f32]
+        L.ref_set_seed.restype = None; L.ref_set_seed.argtypes = [C.c_uint64]
         L.ref_vcm_stage.argtypes = [vp, i32, i32, i32, f32, i32, i32, i32, i32, f32, i32, i32, i32, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp]
         _ref = L
     return _ref
@@ -154,8 +180,8 @@ def scene_path(name):
 class RefScene:
     """A scene loaded by the reference's own loader + SBVH builder + adapters."""
 
-    def __init__(self, scene_file, gpu_layout=False):
-        self.L = ref()
+    def __init__(self, scene_file, gpu_layout=False, lib=None):
+        self.L = lib or ref()
         self.h = self.L.ref_scene_load(scene_file.encode(), int(gpu_layout))
         if not self.h:
             raise RuntimeError(f"reference loader failed on {scene_file}")
@@ -198,6 +224,16 @@ class RefScene:
                                radius_factor, img.ctypes.data, stats.ctypes.data, C.byref(secs), C.byref(px))
         assert rc == 0
         return img, {"primary_rays": int(stats[0]), "shadow_rays": int(stats[1]), "seconds": secs.value, "pixel_size": px.value}
+
+    def render_plugin(self, mode, algo, w, h, fov=60.0, spp=1, iterations=1, threads=0, tile=256, max_path_len=10, light_paths=0, connections=1,
+                      knn=10, radius_factor=2.0, seed=1):
+        """libimba_ref_b200.so only: mode 0 = the reference's integrators on imba::B200WavefrontScheduler, mode 1 = imba::B200Integrator
+        (include/imba_b200_ref.hpp), both driven through the reference's Integrator interface."""
+        img = np.zeros((h, w, 3), np.float32); stats = np.zeros(2, np.uint64); px = np.zeros(2, np.float32)
+        rc = self.L.ref_render_plugin(self.h, mode, algo, w, h, fov, spp, iterations, threads or os.cpu_count(), tile, max_path_len, light_paths, connections, knn,
+                                      radius_factor, seed, img.ctypes.data, stats.ctypes.data, px.ctypes.data)
+        assert rc == 0, rc
+        return img, {"primary_rays": int(stats[0]), "shadow_rays": int(stats[1]), "pixel_size": float(px[0]), "device_pixel_size": float(px[1])}
 
     def light_emit(self, light_ids, rng_states, mis_eta_vc):
         """Light::sample_emit + initial VCM weights of the reference for (light, RNG state) pairs (ref_driver.cpp: ref_vcm_light_emit)."""

@@ -166,3 +166,17 @@ def test_headless_driver_prints_reference_report_line_and_matches_golden(tmp_pat
     assert m and int(m.group(2)) == 128
     rmse = float(re.search(r"RMSE ([\d.e+-]+)", r.stdout).group(1))
     assert rmse < 0.05 and os.path.exists(out)
+
+
+def test_cpp_ray_queue_mirror_against_the_reference_loops(tmp_path):
+    """include/imba_b200.hpp RayQueue (ray_queue.h:58-360): thread-safe push from 8 threads, range push, append, and
+    compact_hits / sort_by_material / compact_rays delegated to the device (imba_queue_*_host), checked by a C++ program against
+    serial restatements of the reference's loops."""
+    import subprocess
+    from tests.conftest import ROOT
+    exe = str(tmp_path / "ray_queue_test")
+    lib_dir = os.path.dirname(abi.LIB_PATH)
+    subprocess.run(["/usr/bin/g++", "-std=c++11", "-O1", "-Wall", "-pthread", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "cpp", "ray_queue_test.cpp"),
+                    "-o", exe, "-L", lib_dir, "-limba_b200", f"-Wl,-rpath,{lib_dir}"], check=True)
+    r = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0 and r.stdout.strip().endswith("ok"), (r.returncode, r.stdout[-2000:])
