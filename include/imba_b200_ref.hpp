@@ -79,6 +79,9 @@ public:
         check(imba_integrator_clear(h_), "clear");
         check(imba_integrator_render(h_, 1), "render");
         check(imba_integrator_download(h_, staging_.data()), "download");
+        uint64_t rays[2];                            // (imba_integrator_clear also restarts the device's ray counters)
+        check(imba_integrator_ray_counts(h_, rays), "ray_counts");
+        total_rays_[0] += rays[0]; total_rays_[1] += rays[1];
         const int n = settings_.width * settings_.height;
         for (int i = 0; i < n; ++i)
             out.pixels()[i].apply<std::plus<float> >(rgb(staging_[3 * i], staging_[3 * i + 1], staging_[3 * i + 2]));
@@ -99,7 +102,8 @@ public:
     }
 
     float device_pixel_size() const { return imba_integrator_pixel_size(h_); }
-    void ray_counts(uint64_t out[2]) { check(imba_integrator_ray_counts(h_, out), "ray_counts"); }
+    /// Primary and shadow rays of all render() calls so far, like TileScheduler's counters (tile_scheduler.h:59-60,117-127).
+    void ray_counts(uint64_t out[2]) const { out[0] = total_rays_[0]; out[1] = total_rays_[1]; }
     imba_integrator* handle() const { return h_; }
 
 private:
@@ -109,6 +113,7 @@ private:
     imba_render_settings settings_;
     imba_integrator* h_;
     std::vector<float> staging_;
+    uint64_t total_rays_[2] = { 0, 0 };
 };
 
 /// One wavefront per frame: a single primary queue over every sample RayGen produces, traversal on the device through the

@@ -64,7 +64,7 @@ def ref_b200():
         L.ref_scene_free.restype = None; L.ref_scene_free.argtypes = [vp]
         L.ref_render.argtypes = [vp, i32, i32, i32, f32] + [i32] * 8 + [f32, vp, vp, vp, vp]
         L.ref_set_seed.restype = None; L.ref_set_seed.argtypes = [C.c_uint64]
-        L.ref_render_plugin.argtypes = [vp, i32, i32, i32, i32, f32] + [i32] * 9 + [f32, C.c_uint32, vp, vp, vp]
+        L.ref_render_plugin.argtypes = [vp, i32, i32, i32, i32, f32] + [i32] * 8 + [f32, C.c_uint32, vp, vp, vp]
         assert L.ref_is_linked_to_product() == 1
         _ref_b200 = L
     return _ref_b200
