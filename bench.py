@@ -151,14 +151,29 @@ def measured_peak_hbm():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def kernel_source_hash():
+    """SHA-256 (first 16 hex digits) of the sources the traversal kernel and its data layout are compiled from: what a committed
+    ncu capture must have been taken on to describe the kernel this run times."""
+    import hashlib
+    h = hashlib.sha256()
+    for f in ("traverse.cu", "traverse_core.cuh", "bvh8.h", "bvh8_build.cpp"):
+        h.update(open(os.path.join(ROOT, "imbatracer_b200", "csrc", f), "rb").read())
+    return h.hexdigest()[:16]
+
+
 def ncu_traffic():
     """dram__bytes_read.sum + dram__bytes_write.sum of the incoherent closest-hit launch, from the last `ncu --set full` capture of
-    this command (tools/ncu_summary.py writes the file); None if no capture has been committed for the current workload."""
+    this workload (tools/ncu_summary.py writes profiles/ncu_traffic.json and stamps it with kernel_source_hash()).  A capture taken
+    on other kernel sources or another workload is REFUSED (None): a stale constant would go unnoticed otherwise."""
     p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if not os.path.exists(p):
-        return None
+        return None, "no capture committed"
     t = json.load(open(p))
-    return t.get("dram_bytes_per_launch") if t.get("workload") == SCENE else None
+    if t.get("workload") != SCENE:
+        return None, f"capture is of workload {t.get('workload')!r}"
+    if t.get("kernel_source_hash") != kernel_source_hash():
+        return None, f"capture was taken on kernel sources {t.get('kernel_source_hash')}, this tree is {kernel_source_hash()}: re-run tools/gpu_round.sh full"
+    return t.get("dram_bytes_per_launch"), f"{t.get('source')} (kernel sources {t.get('kernel_source_hash')})"
 
 
 def cpu_arm(flat, batches, sample, threads):
@@ -213,13 +228,37 @@ def ours_cfg0():
             "samples_per_s": n / dt, "seconds": dt, "mean_radiance": float(img.mean()) / CFG0["spp"]}
 
 
+def reference_built_flat():
+    """The bench scene with the acceleration structure the REFERENCE builds for it: the procedural mesh is written as OBJ / MTL /
+    TGA / .scene (tests/obj_export.py), read back by the reference's own loader and built by its SplitBvhBuilder + GPU adapter
+    (unmodified sources in oracle/_ref/libimba_ref.so; ~25 s for 1.5 M triangles, cached as .bvh by the loader itself,
+    render/scene.cpp:67).  Returns (flat scene in the reference's BVH2 layout, description) or (None, reason)."""
+    from tests import refapi
+    if not refapi.have_ref():
+        return None, "oracle/_ref/libimba_ref.so not built"
+    from imbatracer_b200 import procedural
+    from tests import obj_export
+    d = os.path.join(refapi.REF_SCENES, f"stilllife_proxy_d{PROXY_DETAIL:g}")
+    scene_file = os.path.join(d, "stilllife_proxy.scene")
+    if not os.path.exists(scene_file):
+        os.makedirs(refapi.REF_SCENES, exist_ok=True)
+        obj_export.write_scene(procedural.still_life_proxy(PROXY_DETAIL, accel=None), d)
+    t0 = time.perf_counter()
+    rs = refapi.RefScene(scene_file, True)
+    flat = rs.flat(SCENE)
+    rs.close()
+    return flat, f"reference loader + SplitBvhBuilder + gpu_adapter (BVH2), {time.perf_counter() - t0:.1f} s"
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import __graft_entry__ as g
     g.build()
-    flat = load_flat()
+    flat, tree = reference_built_flat()
+    if flat is None:   # no reference build on this box: the product's host builder, same layout
+        flat, tree = load_flat(), "product host builder (binned SAH, BVH2 layout): " + tree
     cores = os.cpu_count()
     n = RAYS_PER_BATCH  # the full workload: about 4 s of host time per step
     batches = make_batches(flat, n, 0x1234ABCD)
@@ -234,7 +273,8 @@ def run_reference(args):
             "ms_per_step": secs / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": workload_config(flat, n),
             "cpu_baseline": {"value": v, "unit": "Mrays/s", "cores": cores, "kind": "port",
-                             "sample": f"4 batches x {n} rays per step (oracle/traversal_oracle.cpp on the reference BVH2 layout; the AnyDSL kernels are not in the reference tree)"},
+                             "sample": f"4 batches x {n} rays per step; traversal = oracle/traversal_oracle.cpp, a SCALAR std::thread restatement of the four entry "
+                                       f"points (the AnyDSL kernels are not in the reference tree); acceleration structure = {tree}"},
             "e2e": {"value": v, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
 
@@ -243,16 +283,20 @@ def workload_config(flat, n):
     return {"workload": f"traversal micro-bench on the {SCENE} BVH (procedural stand-in for Still Life, whose geometry is absent from the reference "
                         f"tree: camera of still_life.scene, the 23 materials of still_life.mtl, {flat.tri_count} triangles, reference BVH2 layout): per step {n} coherent primary + {n} diffuse-bounce closest-hit rays and "
                         f"{n} + {n} shadow rays", "rays_per_step": 4 * n, "l2_policy": "inputs larger than L2 (each ray queue is 128 MiB, each hit queue 64 MiB)",
-            "parallelism": "independent ray queues per GPU, no collective"}
+            "parallelism": "independent ray queues per GPU, no collective (value, e2e); PT: progressive iterations sharded over the ranks, one NCCL sum of the framebuffer per step (config.pt_*)"}
 
 
-def run_pt(scene, flat, rank, world, barrier, dist, iters, width=1920, height=1080, spp=1, per_pass=1):
+def run_pt(scene, flat, rank, world, barrier, dist, iters, width=1920, height=1080, spp=1, per_pass=1, overlap=None):
+    """configs[2]: progressive PT, iterations sharded over the ranks (rank r renders iterations r, r + R, ...), one NCCL sum of the
+    W x H x 3 float framebuffer per step of `per_pass` iterations.  `iters` = iterations PER RANK inside the timed region.
+    overlap=None: the sum of step k runs on a second stream beside the rendering of step k + 1 (the default of ProgressiveRenderer
+    with more than one rank); overlap=False: render, sum, render, sum ... on one stream."""
     import torch
     from imbatracer_b200 import api
     integ = api.Integrator(scene, api.render_settings(flat, "pt", width, height, spp=spp, max_path_len=10, seed=0x1234ABCD, rank=rank, rank_count=world, iterations_per_pass=per_pass))
     from imbatracer_b200.distributed import ProgressiveRenderer
     integ.preprocess()
-    loop = ProgressiveRenderer(integ, width, height, spp, iterations_per_step=per_pass)   # integ.render(per_pass) + NCCL sum of the framebuffer per iteration (overlapped with the next one)
+    loop = ProgressiveRenderer(integ, width, height, spp, iterations_per_step=per_pass, overlap=overlap)   # integ.render(per_pass) + NCCL sum of the framebuffer per step
     stream = loop.stream
     warm = 2 * per_pass
     loop.step(warm)
@@ -273,9 +317,51 @@ def run_pt(scene, flat, rank, world, barrier, dist, iters, width=1920, height=10
     mean = float(total.mean()) / ((iters + warm) * world * spp)
     integ.close()
     samples = width * height * spp * iters * world
-    return {"workload": f"PT {width}x{height}, {spp} spp per iteration per GPU (the reference's --spp), max path length 10, {SCENE}", "iterations": iters,
+    return {"workload": f"PT {width}x{height}, {spp} spp per iteration per GPU (the reference's --spp), max path length 10, {SCENE}", "iterations_per_rank": iters,
+            "total_spp": iters * world * spp, "seconds": ms * 1e-3,
             "samples_per_s": samples / (ms * 1e-3), "ms_per_iteration": ms / iters, "mrays_s_per_gpu": (prim + shad) / (iters + warm) * iters / (ms * 1e-3) / 1e6, "iterations_per_pass": per_pass,
-            "framebuffer_allreduce_bytes": width * height * 12 if dist is not None else 0, "mean_radiance": mean}
+            "framebuffer_allreduce_bytes": width * height * 12 if dist is not None else 0, "overlap": bool(loop.overlap), "mean_radiance": mean}
+
+
+def measure_allreduce(dist, width=1920, height=1080, reps=20):
+    """The collective alone: NCCL sum of one W x H x 3 float framebuffer, CUDA events on the stream it is enqueued on, max over ranks."""
+    import torch
+    if dist is None:
+        return 0.0
+    fb = torch.zeros(width * height * 3, dtype=torch.float32, device="cuda")
+    comm = torch.cuda.Stream()
+    with torch.cuda.stream(comm):
+        for _ in range(3):
+            dist.all_reduce(fb, op=dist.ReduceOp.SUM)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(comm)
+        for _ in range(reps):
+            dist.all_reduce(fb, op=dist.ReduceOp.SUM)
+        e1.record(comm)
+    comm.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / reps], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t[0])
+
+
+def parity_sample(flat, scene, batches, stride=16):
+    """After the timed regions: every `stride`-th ray of each bench batch re-traced by the CUDA path and by the CPU oracle (the
+    checker, never the thing measured).  Closest hit: whole 16-byte records compared; occlusion: the hit / miss flag."""
+    import torch
+    from imbatracer_b200 import api
+    from tests import refapi
+    checked = mismatches = 0
+    per_batch = {}
+    for name, any_hit in BATCH_ORDER:
+        r = np.ascontiguousarray(batches[name][::stride])
+        got = api.hits_from_device(scene.trace(api.rays_to_device(r), any_hit=bool(any_hit)))
+        torch.cuda.synchronize()
+        want = refapi.trace_oracle(flat, r, any_hit=bool(any_hit))
+        bad = int(((got["tri_id"] >= 0) != (want["tri_id"] >= 0)).sum()) if any_hit else int((got.view(np.uint8).reshape(-1, 16) != want.view(np.uint8).reshape(-1, 16)).any(1).sum())
+        checked += len(r); mismatches += bad; per_batch[name] = bad
+    return {"checked": checked, "mismatches": mismatches, "per_batch": per_batch, "stride": stride,
+            "note": "CUDA path vs oracle/traversal_oracle.cpp on the same rays: closest hit bit-exact (tri_id, inst_id, t, u), occlusion flag-equal; the only known "
+                    "exceptions are the 4 coplanar shadow rays of the full incoherent batch (tests/test_bench_parity_gpu.py)"}
 
 
 def run_integrators(scene, flat, width=1920, height=1080, iters=4):
@@ -380,11 +466,42 @@ def run_extra_scenes(rank):
     return out
 
 
+def bind_to_gpu_numa_node(local):
+    """One process per GPU: run (and first-touch the pinned host queues) on the cores of the GPU's own NUMA node, so that eight
+    ranks do not stream their 48 bytes per ray across the socket interconnect.  Returns a description for the bench line."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * w + b for w, bits in enumerate(words) for b in range(64) if (bits >> b) & 1}
+        allowed = cpus & os.sched_getaffinity(0)
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return f"{len(allowed)} cores of the GPU's NUMA node ({min(allowed)}-{max(allowed)})"
+        return "GPU-local cores not in this process's cpuset: not bound"
+    except Exception as e:   # no NVML / no permission: run unbound
+        return f"not bound ({type(e).__name__})"
+
+
+def host_copy_bandwidth(barrier, mib=256, reps=4):
+    """Plain host memory copy bandwidth of this rank while all ranks copy at the same time (GB/s, read + write bytes): the ceiling
+    the host-queue path shares between the ranks, beside the per-GPU PCIe rate."""
+    a = np.ones(mib << 18, np.float32); b = np.empty_like(a)
+    np.copyto(b, a)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        np.copyto(b, a)
+    return 2 * a.nbytes * reps / (time.perf_counter() - t0) / 1e9
+
+
 def run_ours(args):
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    binding = bind_to_gpu_numa_node(local) if world > 1 and not os.environ.get("IMBA_BENCH_NO_BIND") else "single rank: not bound"
     import torch
     import torch.distributed as dist
     from imbatracer_b200 import abi, api
-    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local)
@@ -452,18 +569,24 @@ def run_ours(args):
         e2e_step()
     barrier()
     e2e_s = time.perf_counter() - t0
-    # configs[2]: PT 1920x1080 progressive, samples sharded over ranks, one NCCL sum of the float framebuffer per iteration
-    # 8 progressive iterations per wavefront pass (imba_render_settings::iterations_per_pass) and per framebuffer sum; every path
-    # keeps the seed of its own iteration, the image is that of single passes -- which `pt_single_pass` times for comparison
-    pt = run_pt(scene, flat, rank, world, barrier, dist if world > 1 else None, iters=8 * max(1, min(args.steps // 4, 4)), per_pass=8)
-    pt_single = run_pt(scene, flat, rank, world, barrier, dist if world > 1 else None, iters=max(4, min(args.steps * 2, 32)))
+    host_bw = host_copy_bandwidth(barrier) if world > 1 else 0.0
+    # configs[2] AS STATED: PT 1920x1080, 256 spp IN TOTAL split over the ranks (strong scaling), one NCCL sum of the float framebuffer
+    # per step.  8 progressive iterations per wavefront pass (imba_render_settings::iterations_per_pass) and per sum; every path keeps
+    # the seed of its own iteration, the image is that of single passes -- which `pt_single_pass` times for comparison
+    d = dist if world > 1 else None
+    pt = run_pt(scene, flat, rank, world, barrier, d, iters=256 // world, per_pass=8)
+    pt_serial = run_pt(scene, flat, rank, world, barrier, d, iters=256 // world, per_pass=8, overlap=False) if world > 1 else pt
+    pt_single = run_pt(scene, flat, rank, world, barrier, d, iters=max(4, min(args.steps * 2, 32)))
     # the same with 4 samples per pixel per wavefront pass: larger wavefronts amortise the tails of the late, small waves
-    pt_spp4 = run_pt(scene, flat, rank, world, barrier, dist if world > 1 else None, iters=max(2, min(args.steps, 8)), spp=4)
+    pt_spp4 = run_pt(scene, flat, rank, world, barrier, d, iters=max(2, min(args.steps, 8)), spp=4)
+    allreduce_ms = measure_allreduce(d)
     sampler.stop_flag = True; sampler.join(timeout=2)
 
     t = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+    bw = torch.tensor([host_bw], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(bw, op=dist.ReduceOp.SUM)
     ms, e2e_ms = float(t[0]), float(t[1])
     total_rays = 4 * n * args.steps * world
     value = total_rays / (ms * 1e-3) / 1e6
@@ -484,26 +607,52 @@ def run_ours(args):
         cores = os.cpu_count()
         sample = 1 << 20
         cpu_total, cpu_secs = cpu_arm(flat, batches, sample, cores)
+        port = {"value": cpu_total / cpu_secs / 1e6, "unit": "Mrays/s", "cores": cores, "kind": "port",
+                "sample": f"first {sample} rays of each of the 4 batches, oracle/traversal_oracle.cpp (scalar restatement of the four entry points) with {cores} threads, "
+                          f"on the same BVH2 structure the CUDA path converted"}
+        # the record's CPU baseline = the reference's OWN host pipeline (N = 1 only: its loader, SBVH builder, TileScheduler, RayQueue and
+        # PathTracer, unmodified, from oracle/_ref) on BASELINE.json configs[0]; the traversal inside it is the scalar restatement,
+        # because the AnyDSL kernels are not in the reference tree.  The traversal-only figure stays beside it.
+        ref0 = reference_cfg0(cores) if world == 1 else {"unavailable": "timed at N = 1 only"}
+        if "mrays_s" in ref0:
+            cpu_baseline = {"value": ref0["mrays_s"], "unit": "Mrays/s", "cores": cores, "kind": "reference",
+                            "sample": ref0["workload"] + f"; {ref0['seconds']:.2f} s, {ref0['samples_per_s'] / 1e6:.2f} M samples/s; unmodified reference host pipeline (TileScheduler + PathTracer, "
+                                      "oracle/_ref), its traversal entry points = the scalar restatement oracle/traversal_oracle.cpp",
+                            "traversal_only": port}
+        else:
+            cpu_baseline = dict(port, reference_pipeline=ref0)
         device_build = device_build_entry(flat, dev["incoherent_closest"], hits["incoherent_closest"], n)
         device_build["rays"] = "the incoherent closest-hit batch"
+        traffic, traffic_src = ncu_traffic()
+        config = workload_config(flat, n)
+        config.update({"pt_workload": "configs[2]: PT 1920x1080, 256 spp in total split over the ranks (strong scaling), max path length 10, 8 iterations per wavefront pass and per "
+                                      "framebuffer sum, on " + SCENE,
+                       "pt_total_spp": pt["total_spp"], "pt_seconds": pt["seconds"], "pt_samples_per_s": pt["samples_per_s"], "pt_ms_per_iteration": pt["ms_per_iteration"],
+                       "pt_ms_per_iteration_no_overlap": pt_serial["ms_per_iteration"], "pt_samples_per_s_no_overlap": pt_serial["samples_per_s"],
+                       "allreduce_bytes": pt["framebuffer_allreduce_bytes"], "allreduce_ms": allreduce_ms,
+                       "allreduce_note": "NCCL sum of the 1920x1080x3 float framebuffer, timed alone on its stream (max over ranks); in the PT loop it runs once per 8 iterations, "
+                                         "overlapped with the next pass (pt_ms_per_iteration) or not (pt_ms_per_iteration_no_overlap)",
+                       "pt_single_pass_samples_per_s": pt_single["samples_per_s"], "pt_mean_radiance": pt["mean_radiance"]})
         line = {"metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-                "data": "synthetic", "config": workload_config(flat, n),
+                "data": "synthetic", "config": config,
                 "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": 4 * n * 32, "d2h_bytes_per_step": 4 * n * 16,
-                        "steps": e2e_steps, "note": "imba_trace_host on pinned host queues from 4 host threads (one per queue), wall clock"},
+                        "steps": e2e_steps, "note": "imba_trace_host on pinned host queues from 4 host threads (one per queue), wall clock",
+                        "pcie_gb_s_per_gpu": e2e_value * 1e6 * 48 / 1e9 / world, "host_cores": os.cpu_count(), "cpu_binding_rank0": binding,
+                        "host_copy_gb_s_all_ranks": float(bw[0]) if world > 1 else None},
                 "gpu_launches": int(launches),
                 "clocks": sampler.summary(),
-                "pt": pt, "pt_single_pass": pt_single, "pt_spp4": pt_spp4, "cfg0": ours_cfg0(), "integrators": run_integrators(scene, flat), "scenes": run_extra_scenes(rank), "device_build": device_build,
+                "parity_sample": parity_sample(flat, scene, batches),
+                "pt": pt, "pt_no_overlap": pt_serial, "pt_single_pass": pt_single, "pt_spp4": pt_spp4, "cfg0": ours_cfg0(), "integrators": run_integrators(scene, flat), "scenes": run_extra_scenes(rank), "device_build": device_build,
                 "per_kernel": {name: {"ms": per_kernel_ms[i], "mrays_s": n / per_kernel_ms[i] / 1e3} for i, (name, _) in enumerate(BATCH_ORDER)},
-                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(),
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
                              "kernel": "trace_kernel<closest> on the incoherent batch", "peak_source": peak_src,
                              "bytes_per_ray": bytes_per_ray, "nodes_per_ray": c[0], "tris_per_ray": c[1], "instances_per_ray": c[2],
                              "algorithmic_bytes_per_launch": bytes_per_ray * n, "structure_bytes": int(scene.stats()["bytes"]),
                              "note": "algorithmic bytes = ray 32 + hit 16 + 80/node + 48/triangle + 64/instance fetched (counted by the instrumented kernel on "
-                                     "this batch); traffic = dram bytes of the same launch from the committed ncu capture (profiles/ncu_traffic.json), "
-                                     "the difference is what L1/L2 serve"},
-                "cpu_baseline": {"value": cpu_total / cpu_secs / 1e6, "unit": "Mrays/s", "cores": cores, "kind": "port",
-                                 "sample": f"first {sample} rays of each of the 4 batches, oracle/traversal_oracle.cpp with {cores} threads"}}
+                                     "this batch); traffic = dram bytes of the same launch from the committed ncu capture (profiles/ncu_traffic.json, refused unless it was "
+                                     "taken on the same kernel sources); the difference is what L1/L2 serve -- the kernel is issue-bound, not HBM-bound (DESIGN.md section 3)"},
+                "cpu_baseline": cpu_baseline}
     scene.close()
     if world > 1:
         dist.barrier(); dist.destroy_process_group()

@@ -50,7 +50,9 @@ def main():
         if len(pick) == 1:
             i = pick[0]
             val = lambda m: float(data[i][hdr.index(m)].replace(",", "")) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[units[hdr.index(m)]]
-            t = {"workload": sys.argv[3], "kernel": names[i], "dram_bytes_per_launch": val("dram__bytes_read.sum") + val("dram__bytes_write.sum"),
+            sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+            import bench
+            t = {"workload": sys.argv[3], "kernel": names[i], "kernel_source_hash": bench.kernel_source_hash(), "dram_bytes_per_launch": val("dram__bytes_read.sum") + val("dram__bytes_write.sum"),
                  "dram_read": val("dram__bytes_read.sum"), "dram_write": val("dram__bytes_write.sum"), "source": os.path.basename(out)}
             json.dump(t, open(os.path.join(os.path.dirname(out), "ncu_traffic.json"), "w"), indent=1)
             print("traffic", t)
