@@ -142,7 +142,13 @@ def lib():
     L.imba_integrator_destroy.restype = None; L.imba_integrator_destroy.argtypes = [vp]
     L.imba_integrator_preprocess.argtypes = [vp]
     L.imba_integrator_pixel_size.restype = f32; L.imba_integrator_pixel_size.argtypes = [vp]
+    L.imba_integrator_vertex_cache_size.argtypes = [vp]
     L.imba_integrator_reset.argtypes = [vp]
+    L.imba_integrator_set_camera.argtypes = [vp, vp, vp, vp]
+    L.imba_integrator_allreduce.argtypes = [vp, vp, vp]
+    L.imba_queue_compact_hits_host.argtypes = [vp, vp, vp, i32, i32, vp]
+    L.imba_queue_compact_rays_host.argtypes = [vp, vp, i32, i32, vp]
+    L.imba_queue_sort_keys_host.argtypes = [vp, i32, i32, vp]
     L.imba_integrator_render.argtypes = [vp, i32]
     L.imba_integrator_framebuffer.restype = vp; L.imba_integrator_framebuffer.argtypes = [vp]
     L.imba_integrator_set_framebuffer.argtypes = [vp, vp]

@@ -113,6 +113,37 @@ extern "C" int imba_integrator_set_framebuffer(imba_integrator* it, float* d_rgb
 
 extern "C" void* imba_integrator_stream(imba_integrator* it) { return it ? (void*)it->stream : nullptr; }
 
+/* The one collective of the multi-GPU path, for host programs that are not Python: sums the integrator's W x H x 3
+ * float framebuffer over all ranks of `nccl_comm` in place (ncclAllReduce, ncclFloat32, ncclSum).  The library does not link
+ * NCCL: the host program created the communicator, so its NCCL is in the process already and is looked up at the first call
+ * (dlopen RTLD_NOLOAD, then by name).  stream = null: the integrator's own stream, i.e. ordered after the rendering. */
+#include <dlfcn.h>
+typedef int (*NcclAllReduceFn)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+static NcclAllReduceFn nccl_allreduce_fn() {
+    static NcclAllReduceFn fn = nullptr;
+    static std::mutex m;
+    std::lock_guard<std::mutex> lock(m);
+    if (fn) return fn;
+    fn = (NcclAllReduceFn)dlsym(RTLD_DEFAULT, "ncclAllReduce");           // linked into the host program or loaded RTLD_GLOBAL
+    const char* names[] = { "libnccl.so.2", "libnccl.so" };
+    for (int pass = 0; pass < 2 && !fn; ++pass)
+        for (const char* n : names) {
+            void* h = dlopen(n, RTLD_NOW | (pass == 0 ? RTLD_NOLOAD : RTLD_GLOBAL));
+            if (h && (fn = (NcclAllReduceFn)dlsym(h, "ncclAllReduce"))) break;
+        }
+    return fn;
+}
+
+extern "C" int imba_integrator_allreduce(imba_integrator* it, void* nccl_comm, void* stream) {
+    if (!it || !nccl_comm) { imba_set_error("null argument"); return IMBA_ERR_INVALID; }
+    NcclAllReduceFn fn = nccl_allreduce_fn();
+    if (!fn) { imba_set_error("ncclAllReduce not found: no NCCL library in this process (%s)", dlerror() ? dlerror() : "libnccl.so.2"); return IMBA_ERR_INVALID; }
+    const size_t count = (size_t)it->cfg.width * it->cfg.height * 3;
+    const int rc = fn(it->fb, it->fb, count, 7 /* ncclFloat32 */, 0 /* ncclSum */, nccl_comm, stream ? (cudaStream_t)stream : it->stream);
+    if (rc != 0) { imba_set_error("ncclAllReduce failed with ncclResult_t %d", rc); return IMBA_ERR_CUDA; }
+    return IMBA_OK;
+}
+
 extern "C" int imba_integrator_preprocess(imba_integrator* it) {
     if (!it) { imba_set_error("null argument"); return IMBA_ERR_INVALID; }
     const int quads = ((it->cam.width + 7) / 8) * ((it->cam.height + 7) / 8);
@@ -136,6 +167,7 @@ extern "C" int imba_integrator_preprocess(imba_integrator* it) {
 }
 
 extern "C" float imba_integrator_pixel_size(const imba_integrator* it) { return it ? it->pixel_size : 0.0f; }
+extern "C" int imba_integrator_vertex_cache_size(const imba_integrator* it) { return it ? it->cache_capacity : 0; }
 extern "C" int imba_integrator_reset(imba_integrator* it) { if (!it) return IMBA_ERR_INVALID; it->iteration = 0; return IMBA_OK; }
 
 /* Camera moved (CameraControl -> PerspectiveCamera::move, camera.h:27-50; the reference then calls Integrator::reset,

@@ -21,7 +21,7 @@
 #include "vecmath.cuh"
 
 enum { BSDF_NONE = 0, BSDF_REFLECTION = 1, BSDF_TRANSMISSION = 2, BSDF_DIFFUSE = 4, BSDF_GLOSSY = 8, BSDF_SPECULAR = 16 };
-enum { MAT_DIFFUSE = 0, MAT_MIRROR = 1, MAT_GLASS = 2, MAT_GLOSSY = 3 };
+enum { MAT_DIFFUSE = 0, MAT_MIRROR = 1, MAT_GLASS = 2, MAT_GLOSSY = 3, MAT_PHONG = 4 };
 enum { LIGHT_TRIANGLE = 0, LIGHT_DIRECTIONAL = 1, LIGHT_POINT = 2, LIGHT_SPOT = 3, LIGHT_ENV = 4 };
 
 struct DevLight {            // 7 x float4
@@ -168,7 +168,32 @@ struct Bsdf {
     __device__ __forceinline__ bool is_specular() const { return kind == MAT_MIRROR || kind == MAT_GLASS; } // Material::is_specular
     __device__ __forceinline__ int brdf_flags() const {
         return kind == MAT_DIFFUSE ? (BSDF_DIFFUSE | BSDF_REFLECTION)
-             : kind == MAT_GLOSSY  ? (BSDF_GLOSSY | BSDF_DIFFUSE | BSDF_REFLECTION) : (BSDF_SPECULAR | BSDF_REFLECTION);
+             : kind == MAT_GLOSSY  ? (BSDF_GLOSSY | BSDF_DIFFUSE | BSDF_REFLECTION)
+             : kind == MAT_PHONG   ? (BSDF_GLOSSY | BSDF_REFLECTION) : (BSDF_SPECULAR | BSDF_REFLECTION);
+    }
+    // Phong (brdfs.h:48-92): lobe of power `exponent` about the mirrored direction, coefficient ks.  Quirks kept: eval mirrors the
+    // INCOMING direction, pdf() is the power-cosine density of in_dir.z (about the normal, not about the mirrored direction).
+    __device__ __forceinline__ V3 phong_eval(V3 o, V3 i) const {
+        const V3 reflected_in = v3(-i.x, -i.y, i.z);
+        float cos_r_o = fmaxf(0.0f, dot(reflected_in, o));
+        cos_r_o = fminf(cos_r_o, 1.0f);
+        return o.z * i.z > 0.0f ? ((exponent + 2.0f) / (2.0f * IMBA_PI)) * ks * powf(cos_r_o, exponent) : v3(0.0f);
+    }
+    __device__ __forceinline__ float phong_pdf(V3 o, V3 i) const {
+        return i.z > 0.0f ? ((exponent + 1.0f) * powf(i.z, exponent) * 1.0f / (2.0f * IMBA_PI)) : 0.0f;
+    }
+    __device__ __forceinline__ V3 phong_sample(V3 o, V3& i, Rng& rng, float& pdf_out) const {
+        const float u2 = rng.uniform(), u1 = rng.uniform();   // sample_power_cos_hemisphere(exponent, u1, u2): arguments right to left
+        const float phi = IMBA_PI * 2.0f * u1;
+        const float cos_t = powf(u2, 1.0f / (exponent + 1.0f));
+        const float sin_t = sqrtf(1.0f - sqr(cos_t));
+        const V3 dir = v3(sin_t * cosf(phi), sin_t * sinf(phi), cos_t);
+        pdf_out = (exponent + 1.0f) * powf(cos_t, exponent) * 1.0f / (2.0f * IMBA_PI);
+        const V3 reflected_in = v3(-o.x, -o.y, o.z);
+        V3 t, b; local_coordinates(reflected_in, t, b);
+        i = v3(b.x * dir.x + t.x * dir.y + reflected_in.x * dir.z, b.y * dir.x + t.y * dir.y + reflected_in.y * dir.z,
+               b.z * dir.x + t.z * dir.y + reflected_in.z * dir.z);
+        return o.z * i.z > 0.0f ? phong_eval(o, i) : v3(0.0f);
     }
     // CookTorrance with a Blinn distribution (brdfs.h:136-226), fresnel = conductor(1, exponent) (materials.h:174)
     __device__ __forceinline__ V3 cook_eval(V3 o, V3 i) const {
@@ -194,11 +219,13 @@ struct Bsdf {
     __device__ __forceinline__ V3 brdf_eval(V3 o, V3 i) const {
         if (kind == MAT_DIFFUSE) return lambert_eval(o, i);
         if (kind == MAT_GLOSSY) return 0.5f * (cook_eval(o, i) + lambert_eval(o, i));
+        if (kind == MAT_PHONG) return phong_eval(o, i);
         return v3(0.0f);
     }
     __device__ __forceinline__ float brdf_pdf(V3 o, V3 i) const {
         if (kind == MAT_DIFFUSE) return lambert_pdf(o, i);
         if (kind == MAT_GLOSSY) return (cook_pdf(o, i) + lambert_pdf(o, i)) * 0.5f;
+        if (kind == MAT_PHONG) return phong_pdf(o, i);
         return 0.0f;
     }
     /* bsdf.h:126-147, 207-222 with flags = BSDF_ALL */
@@ -233,6 +260,7 @@ struct Bsdf {
     __device__ __forceinline__ V3 brdf_sample(V3 o, V3& i, Rng& rng, float& pdf_out) const {
         if (kind == MAT_DIFFUSE) return lambert_sample(o, i, rng, pdf_out);
         if (kind == MAT_GLOSSY) return rng.uniform() < 0.5f ? cook_sample(o, i, rng, pdf_out) : lambert_sample(o, i, rng, pdf_out);
+        if (kind == MAT_PHONG) return phong_sample(o, i, rng, pdf_out);
         // SpecularReflection (brdfs.h:25-45): conductor fresnel for mirrors, dielectric(1, eta) for glass
         i = v3(-o.x, -o.y, o.z);
         pdf_out = 1.0f;
@@ -259,7 +287,7 @@ struct Bsdf {
     /* bsdf.h:149-204 with flags = BSDF_ALL, or (specular_only) SPECULAR | REFLECTION | TRANSMISSION as the PPM camera
      * pass requests (vcm.cpp:141-143): non-specular BRDFs then do not match and nothing is drawn from the RNG */
     __device__ __forceinline__ V3 sample(V3 out_dir, V3& in_dir, Rng& rng, int& sampled_flags, float& pdf_out, bool specular_only = false) const {
-        if (specular_only && (kind == MAT_DIFFUSE || kind == MAT_GLOSSY)) { pdf_out = 0.0f; sampled_flags = 0; return v3(0.0f); }
+        if (specular_only && (kind == MAT_DIFFUSE || kind == MAT_GLOSSY || kind == MAT_PHONG)) { pdf_out = 0.0f; sampled_flags = 0; return v3(0.0f); }
         const V3 lo = to_local(out_dir);
         const float btdf_prob = has_btdf() ? 1.0f - fresnel_dielectric_eval(lo.z, 1.0f, eta) : 0.0f;
         const float rnd = rng.uniform();

@@ -708,7 +708,69 @@ cudaError_t camera_shade(const VcmLaunch& a, cudaStream_t st) {
     return cudaGetLastError();
 }
 
+/* ---- LightVertices::compute_cache_size (light_vertices.cpp:15-129): the reference's sizing probe, restated ----------------------
+ * NOT the light pass above: 10 000 light paths with a plain throughput (radiance / pdf_lightpick, no MIS quantities), Russian
+ * roulette on that throughput, BSDF_ALL sampling with adjoint BSDFs, one count per hit on a non-specular material; the host loop
+ * stops as soon as 256 or fewer paths are left.  Its average is what sizes the vertex cache, so it is this estimator -- not the
+ * mean vertex count of the real light pass, which is up to 10 % higher -- that has to be reproduced. */
+__global__ void vcm_probe_raygen_kernel(const DeviceShading S, uint32_t seed_base, int count, float4* rays, PTState* states, int* count_out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) *count_out = count;
+    if (i >= count) return;
+    // state_out.rng = RNG(rd()): a fresh 32-bit value per path as the 64-bit generator state (light_vertices.cpp:34-35)
+    uint32_t z = seed_base + 0x9E3779B9u * (uint32_t)(i + 1);
+    z = (z ^ (z >> 16)) * 0x85EBCA6Bu; z = (z ^ (z >> 13)) * 0xC2B2AE35u; z ^= z >> 16;
+    Rng rng; rng.s = (uint64_t)z;
+    const int light = rng.range(0, S.light_count);
+    const float pdf_lightpick = 1.0f / S.light_count;
+    const EmitSample s = light_sample_emit(S, light, rng);
+    rays[2 * i] = make_float4(s.pos.x, s.pos.y, s.pos.z, 1e-3f);
+    rays[2 * i + 1] = make_float4(s.dir.x, s.dir.y, s.dir.z, FLT_MAX);
+    const V3 thr = s.radiance / pdf_lightpick;
+    PTState st; st.pixel_id = i; st.sample_id = 0; st.rng = rng.s; st.tr = thr.x; st.tg = thr.y; st.tb = thr.z; st.bounces_spec = 0; st.last_pdf = 0.0f; st.pad = 0;
+    states[i] = st;
+}
+
+__global__ void vcm_probe_shade_kernel(const DeviceShading S, const float4* rays, const int4* hits, const PTState* states, const int* count_ptr,
+                                       float4* out_rays, PTState* out_states, int* out_count, int* vertex_count) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= *count_ptr) return;
+    const int4 h = hits[i];
+    if (h.x < 0) return;                                   // `tri_id < 0 || !russian_roulette(...)`: no random number for a miss
+    PTState st = states[i];
+    Rng rng; rng.s = st.rng;
+    V3 thr = v3(st.tr, st.tg, st.tb);
+    const float rr_pdf = fminf(1.0f, luminance(thr) * 2.0f);
+    if (!(rng.uniform() < rr_pdf)) return;
+    const float4 ro = rays[2 * i], rd = rays[2 * i + 1];
+    const float t = __int_as_float(h.z);
+    const Isect is = calc_intersection(S, ro, rd, h.x, h.y, t, __int_as_float(h.w));
+    const Bsdf bsdf = make_bsdf(S, is, true);
+    if (!bsdf.is_specular()) atomicAdd(vertex_count, 1);   // "we would store a vertex at this position"
+    float pdf_dir_w; V3 dir; int flags;
+    const V3 value = bsdf.sample(is.out_dir, dir, rng, flags, pdf_dir_w);
+    if (flags == 0 || pdf_dir_w == 0.0f || is_black(value)) return;
+    const float cos_theta_i = fabsf(dot(is.normal, dir));
+    thr *= value * cos_theta_i / (rr_pdf * pdf_dir_w);
+    st.tr = thr.x; st.tg = thr.y; st.tb = thr.z; st.rng = rng.s;
+    const int o = queue_push_slot(out_count);
+    out_states[o] = st;
+    out_rays[2 * (size_t)o] = make_float4(is.pos.x, is.pos.y, is.pos.z, t * 1e-3f);
+    out_rays[2 * (size_t)o + 1] = make_float4(dir.x, dir.y, dir.z, FLT_MAX);
+}
+
 } // namespace
+
+cudaError_t imba_vcm_probe_raygen(const DeviceShading& S, uint32_t seed_base, int count, float4* rays, PTState* states, int* count_out, cudaStream_t st) {
+    vcm_probe_raygen_kernel<<<(std::max(count, 1) + 255) / 256, 256, 0, st>>>(S, seed_base, count, rays, states, count_out);
+    return cudaGetLastError();
+}
+cudaError_t imba_vcm_probe_shade(const DeviceShading& S, const float4* rays, const int4* hits, const PTState* states, const int* count_ptr, int capacity,
+                                 float4* out_rays, PTState* out_states, int* out_count, int* vertex_count, cudaStream_t st) {
+    if (capacity <= 0) return cudaSuccess;
+    vcm_probe_shade_kernel<<<(capacity + 127) / 128, 128, 0, st>>>(S, rays, hits, states, count_ptr, out_rays, out_states, out_count, vertex_count);
+    return cudaGetLastError();
+}
 
 cudaError_t imba_vcm_light_raygen(const DeviceShading& S, const VcmParams* P, const PtSeeds& seeds, int per_iteration, int total, float4* rays, VCMState* states, int* count_out, cudaStream_t st) {
     vcm_light_raygen_kernel<<<(std::max(total, 1) + 255) / 256, 256, 0, st>>>(S, P, seeds, per_iteration, total, rays, states, count_out);

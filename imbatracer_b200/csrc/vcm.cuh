@@ -28,6 +28,10 @@ struct VcmLaunch {
     float4* out_rays; VCMState* out_states; int* out_count; // next wavefront's queue (fused compaction)
 };
 
+/* LightVertices::compute_cache_size (light_vertices.cpp:15-129): probe paths and one wavefront of the probe's own shading loop */
+cudaError_t imba_vcm_probe_raygen(const DeviceShading& S, uint32_t seed_base, int count, float4* rays, PTState* states, int* count_out, cudaStream_t st);
+cudaError_t imba_vcm_probe_shade(const DeviceShading& S, const float4* rays, const int4* hits, const PTState* states, const int* count_ptr, int capacity,
+                                 float4* out_rays, PTState* out_states, int* out_count, int* vertex_count, cudaStream_t st);
 cudaError_t imba_vcm_light_raygen(const DeviceShading& S, const VcmParams* P, const PtSeeds& seeds, int per_iteration, int total, float4* rays, VCMState* states, int* count_out, cudaStream_t st);
 cudaError_t imba_vcm_camera_raygen(const DevCamera& cam, const VcmParams* P, int spp, uint32_t seed_base, int count, float4* rays, VCMState* states, int* count_out, cudaStream_t st);
 cudaError_t imba_vcm_light_shade(int algo, const VcmLaunch& a, cudaStream_t st);

@@ -238,31 +238,37 @@ int imba_vcm_allocate(imba_integrator* it) {
 /* VCMIntegrator::preprocess (vcm.h:74-81): base radius from the pixel size; LightVertices::compute_cache_size: trace
  * LIGHT_PATH_LEN_PROBES light paths, count the vertices that would be stored, size the cache to
  * margin * ceil(average) * path_count with margin 1.1 (10 for tiny path counts), light_vertices.cpp:121-128.
- * The probe runs the real light pass (with an empty cache, every append is counted and dropped). */
+ * The probe is the reference's own simplified light tracer (vcm.cu: vcm_probe_*), not the light pass: its average path length is
+ * what the slot count is a step function of (tests/test_vcm_gpu.py compares the counts with the reference's for six scenes). */
 int imba_vcm_preprocess(imba_integrator* it) {
     it->base_radius = it->pixel_size * it->cfg.radius_factor;
     const int algo = it->cfg.algorithm;
     if (algo == IMBA_ALGO_LT || algo == IMBA_ALGO_VCM_PT) { it->cache_capacity = 0; return imba_vcm_allocate(it); }
-    const int probes = std::min(10000, it->capacity);
+    const int probes = std::min(10000, it->capacity);   // LIGHT_PATH_LEN_PROBES (light_vertices.h:61)
     it->cache_capacity = 0;
     int rc = imba_vcm_allocate(it);
     if (rc != IMBA_OK) return rc;
-    VcmParams P = iteration_params(it, 1);
-    rc = set_params(it, P);
-    if (rc != IMBA_OK) return rc;
-    float* saved_fb = it->fb; // the probe must not contribute: let its camera connections go to a scratch accumulator
-    float* scratch = nullptr;
-    IMBA_CUDA(cudaMalloc((void**)&scratch, (size_t)it->cfg.width * it->cfg.height * 3 * sizeof(float)), IMBA_ERR_CUDA);
-    it->fb = scratch;
-    unsigned long long stats[2];
-    IMBA_CUDA(cudaMemcpy(stats, it->d_stats, 16, cudaMemcpyDeviceToHost), IMBA_ERR_CUDA);
-    PtSeeds probe_seed; probe_seed.base[0] = imba_iteration_seed(it->cfg.seed, ~0ull, 3);
-    rc = light_pass(it, IMBA_ALGO_PPM /* cache appends only */, probe_seed, probes, probes, nullptr, false);
-    it->fb = saved_fb; cudaFree(scratch);
-    if (rc != IMBA_OK) return rc;
-    IMBA_CUDA(cudaMemcpy(it->d_stats, stats, 16, cudaMemcpyHostToDevice), IMBA_ERR_CUDA);
+    // the reference's own probe (light_vertices.cpp:15-129; vcm.cu: vcm_probe_*): wavefronts until 256 or fewer paths are left
+    const DeviceShading& S = *imba_shading_view(it->scene);
+    int* d_vertex_count = it->cache_last;   // scratch: nothing is cached yet
+    IMBA_CUDA(cudaMemsetAsync(d_vertex_count, 0, sizeof(int), it->stream), IMBA_ERR_CUDA);
+    IMBA_CUDA(imba_vcm_probe_raygen(S, imba_iteration_seed(it->cfg.seed, ~0ull, 3), probes, it->rays[0], (PTState*)it->states[0], it->count[0], it->stream), IMBA_ERR_CUDA);
+    g_imba_launches.fetch_add(1);
+    int cur = 0, n = probes;
+    for (int wave = 0; n > 256; ++wave, cur ^= 1) {
+        TraceRequest rq; rq.d_rays = (const imba_ray*)it->rays[cur]; rq.d_hits = (imba_hit*)it->hits; rq.capacity = n; rq.d_count = it->count[cur]; rq.mode = 0;
+        if ((rc = imba_scene_trace_ex(it->scene, rq, it->stream)) != IMBA_OK) return rc;
+        IMBA_CUDA(cudaMemsetAsync(it->count[cur ^ 1], 0, sizeof(int), it->stream), IMBA_ERR_CUDA);
+        IMBA_CUDA(imba_vcm_probe_shade(S, it->rays[cur], it->hits, (const PTState*)it->states[cur], it->count[cur], n, it->rays[cur ^ 1], (PTState*)it->states[cur ^ 1],
+                                       it->count[cur ^ 1], d_vertex_count, it->stream), IMBA_ERR_CUDA);
+        g_imba_launches.fetch_add(1);
+        IMBA_CUDA(cudaMemcpyAsync(&n, it->count[cur ^ 1], sizeof(int), cudaMemcpyDeviceToHost, it->stream), IMBA_ERR_CUDA);
+        IMBA_CUDA(cudaStreamSynchronize(it->stream), IMBA_ERR_CUDA);
+        if (wave > 4096) { imba_set_error("cache-size probe did not terminate"); return IMBA_ERR_OVERFLOW; }
+    }
     int vertex_count = 0;
-    IMBA_CUDA(cudaMemcpy(&vertex_count, it->cache_last, sizeof(int), cudaMemcpyDeviceToHost), IMBA_ERR_CUDA);
+    IMBA_CUDA(cudaMemcpy(&vertex_count, d_vertex_count, sizeof(int), cudaMemcpyDeviceToHost), IMBA_ERR_CUDA);
+    IMBA_CUDA(cudaMemset(d_vertex_count, 0, sizeof(int)), IMBA_ERR_CUDA);
     const float avg_len = (float)vertex_count / (float)probes;
     const float margin = (it->cfg.light_path_count < 10000 / 10) ? 10.0f : 1.1f;
     const double size = (double)margin * std::ceil(avg_len) * (double)it->cfg.light_path_count;

@@ -101,7 +101,9 @@ typedef enum { IMBA_ACCEL_MBVH4 = 0, IMBA_ACCEL_BVH2 = 1,
                 * per-mesh trees on the device (linear BVH + SAH-optimal 8-wide collapse) and the small top level on the host;
                 * replaces SplitBvhBuilder (core/sbvh_builder.h) + the adapters for scenes loaded without one */
                IMBA_ACCEL_DEVICE_BUILD = 2 } imba_accel_layout;
-typedef enum { IMBA_MAT_DIFFUSE = 0, IMBA_MAT_MIRROR = 1, IMBA_MAT_GLASS = 2, IMBA_MAT_GLOSSY = 3 } imba_material_kind;
+/* IMBA_MAT_PHONG: a BSDF holding the reference's Phong BxDF (render/materials/brdfs.h:48-92; coefficient = ks, exponent).  No material of
+ * the reference's loader instantiates it (build_scene.cpp:125-161), a host program that does builds BSDF(isect, Phong, nullptr). */
+typedef enum { IMBA_MAT_DIFFUSE = 0, IMBA_MAT_MIRROR = 1, IMBA_MAT_GLASS = 2, IMBA_MAT_GLOSSY = 3, IMBA_MAT_PHONG = 4 } imba_material_kind;
 typedef enum { IMBA_LIGHT_TRIANGLE = 0, IMBA_LIGHT_DIRECTIONAL = 1, IMBA_LIGHT_POINT = 2, IMBA_LIGHT_SPOT = 3,
                IMBA_LIGHT_ENV = 4 } imba_light_kind;
 
@@ -306,6 +308,9 @@ void  imba_integrator_destroy(imba_integrator* it);
 /* Integrator::preprocess (integrator.cpp:14-71 pixel-size probe; light_vertices.cpp:15-129 cache sizing). */
 int   imba_integrator_preprocess(imba_integrator* it);
 float imba_integrator_pixel_size(const imba_integrator* it);
+/* Light-vertex slots the preprocess step allocated: LightVertices::compute_cache_size (light_vertices.cpp:15-129) -- 10 000 probe
+ * light paths, margin * ceil(average stored vertices per path) * light_path_count, margin 1.1 (10 below 1000 paths); 0 for PT / LT. */
+int   imba_integrator_vertex_cache_size(const imba_integrator* it);
 /* Integrator::reset (vcm.h:69-72). */
 int   imba_integrator_reset(imba_integrator* it);
 /* Camera moved (PerspectiveCamera::move, camera.h:27-50, followed by Integrator::reset as render_window.cpp:97-101 does):
@@ -318,6 +323,10 @@ int   imba_integrator_render(imba_integrator* it, int iterations);
 float* imba_integrator_framebuffer(imba_integrator* it);
 /* Makes the integrator accumulate into a caller-owned device buffer (W*H*3 floats), e.g. one registered with NCCL. */
 int   imba_integrator_set_framebuffer(imba_integrator* it, float* d_rgb);
+/* Multi-GPU (one process per GPU, scene replicated, progressive iterations sharded over the ranks by rank / rank_count): sums the
+ * W*H*3 float framebuffer over all ranks of `nccl_comm` (an ncclComm_t of the host program's NCCL) in place, on `stream` (a
+ * cudaStream_t) or, if null, on the integrator's own stream after the rendering enqueued so far.  The single collective of the path. */
+int   imba_integrator_allreduce(imba_integrator* it, void* nccl_comm, void* stream);
 /* The cudaStream_t all work of this integrator is enqueued on; imba_integrator_sync waits for it. */
 void* imba_integrator_stream(imba_integrator* it);
 int   imba_integrator_sync(imba_integrator* it);

@@ -65,6 +65,21 @@ using namespace imba;
 // load_png.cpp needs libpng (absent); the Cornell scenes have no textures.
 namespace imba { bool load_png(const Path&, Image&) { return false; } }
 
+// TEST HOOK for the Phong BxDF (render/materials/brdfs.h:48-92).  The reference defines the class but none of its materials builds
+// one (build_scene.cpp:125-161), so parity needs a material on the reference side that does: BSDF(isect, Phong, nullptr), built in
+// the per-thread arena exactly like DiffuseMaterial builds its Lambertian (materials.h:76-84).
+class PhongTestMaterial : public Material {
+public:
+    PhongTestMaterial(const rgb& coefficient, float exponent) : coefficient_(coefficient), exponent_(exponent) {}
+    Material* duplicate() const override final { return new PhongTestMaterial(coefficient_, exponent_); }
+    BSDF* get_bsdf(const Intersection& isect, MemoryArena& mem_arena, bool adjoint) const override {
+        auto brdf = mem_arena.alloc<Phong>(coefficient_, exponent_);
+        return mem_arena.alloc<BSDF>(isect, brdf, nullptr);
+    }
+    rgb coefficient_; float exponent_;
+};
+
+
 namespace {
 
 struct RefScene {
@@ -207,6 +222,16 @@ void ref_scene_camera(void* h, float* pos, float* dir, float* up) {
     for (int i = 0; i < 3; ++i) { pos[i] = rs->cam_pos[i]; dir[i] = rs->cam_dir[i]; up[i] = rs->cam_up[i]; }
 }
 
+/// LightVertices::compute_cache_size (light_vertices.cpp:15-129) of the reference for `light_path_count` paths: 10 000 probe light
+/// paths traced until fewer than 256 are left; returns the number of vertex slots it allocates (margin 1.1, or 10 for < 1000 paths).
+int ref_vcm_cache_size(void* h, int light_path_count) {
+    Quiet q;
+    auto rs = (RefScene*)h;
+    LightVertices lv(light_path_count);
+    lv.compute_cache_size(*rs->scene, rs->gpu_layout);
+    return (int)lv.cache_.size();
+}
+
 /// Makes the reference's std::random_device reproducible (oracle/shim/det_random.h); 0 = the real device again.
 void ref_set_seed(uint64_t seed) { imba_det::seed(seed); }
 
@@ -278,6 +303,9 @@ int ref_scene_export(void* h, imba_scene_desc* d) {
             o.kind = IMBA_MAT_GLASS; o.eta = p->eta_;
             o.ks[0] = p->reflectance_.x; o.ks[1] = p->reflectance_.y; o.ks[2] = p->reflectance_.z;
             o.tf[0] = p->transmittance_.x; o.tf[1] = p->transmittance_.y; o.tf[2] = p->transmittance_.z;
+        } else if (auto p = dynamic_cast<PhongTestMaterial*>(mat)) {
+            o.kind = IMBA_MAT_PHONG; o.exponent = p->exponent_;
+            o.ks[0] = p->coefficient_.x; o.ks[1] = p->coefficient_.y; o.ks[2] = p->coefficient_.z;
         } else if (auto p = dynamic_cast<GlossyMaterial*>(mat)) {
             o.kind = IMBA_MAT_GLOSSY; o.exponent = p->exponent_; o.diffuse_tex = tid(p->diff_sampler_);
             o.ks[0] = p->specular_color_.x; o.ks[1] = p->specular_color_.y; o.ks[2] = p->specular_color_.z;
@@ -601,6 +629,23 @@ int ref_scene_add_test_textures(void* h, uint64_t seed) {
         Mesh& mesh = sc.meshes()[k];
         auto tc = mesh.attribute<float2>(MeshAttributes::TEXCOORDS);
         for (size_t v = 0; v < mesh.vertex_count(); ++v) { tc[v].x = 4.0f * rng.random_float() - 1.5f; tc[v].y = 4.0f * rng.random_float() - 1.5f; }
+    }
+    return changed;
+}
+
+/// Replaces every non-emissive diffuse / glossy material by a PhongTestMaterial (coefficient from its colour, exponent 4 .. 67).
+int ref_scene_add_test_phong(void* h, uint64_t seed) {
+    auto rs = (RefScene*)h; Scene& sc = *rs->scene;
+    RNG rng(seed);
+    int changed = 0;
+    for (size_t m = 0; m < sc.material_count(); ++m) {
+        Material* mat = sc.material(m).get();
+        if (mat->emitter()) continue;
+        rgb c(0.0f);
+        if (auto d = dynamic_cast<DiffuseMaterial*>(mat)) c = d->sampler_ ? rgb(0.6f, 0.5f, 0.4f) : d->color_;
+        else if (auto g = dynamic_cast<GlossyMaterial*>(mat)) c = g->specular_color_;
+        else continue;
+        sc.materials()[m].reset(new PhongTestMaterial(0.25f * c + rgb(0.05f), 4.0f + floorf(64.0f * rng.random_float()))); ++changed;
     }
     return changed;
 }

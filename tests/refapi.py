@@ -90,7 +90,9 @@ def ref():
         L.ref_vcm_camera_start.argtypes = [vp, i32, i32, f32, i32, i32, vp, vp, vp, vp]
         L.ref_scene_add_test_textures.argtypes = [vp, C.c_uint64]
         L.ref_scene_add_test_envmap.argtypes = [vp, C.c_uint64, f32]
+        L.ref_scene_add_test_phong.argtypes = [vp, C.c_uint64]
         L.ref_set_seed.restype = None; L.ref_set_seed.argtypes = [C.c_uint64]
+        L.ref_vcm_cache_size.argtypes = [vp, i32]
         L.ref_vcm_stage.argtypes = [vp, i32, i32, i32, f32, i32, i32, i32, i32, f32, i32, i32, i32, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp]
         _ref = L
     return _ref
@@ -195,6 +197,10 @@ class RefScene:
         """Procedural colour / bump textures + texcoords on the reference side (oracle/ref_driver.cpp); export with flat() afterwards."""
         return self.L.ref_scene_add_test_textures(self.h, seed)
 
+    def add_test_phong(self, seed=17):
+        """Replaces the diffuse / glossy materials by materials that build the reference's Phong BxDF (brdfs.h:48-92); export with flat()."""
+        return self.L.ref_scene_add_test_phong(self.h, seed)
+
     def add_test_envmap(self, seed=5, intensity=0.8):
         """Procedural lat-long environment map + EnvLight on the reference side; export with flat() afterwards."""
         return self.L.ref_scene_add_test_envmap(self.h, seed, intensity)
@@ -234,6 +240,10 @@ class RefScene:
                                       radius_factor, seed, img.ctypes.data, stats.ctypes.data, px.ctypes.data)
         assert rc == 0, rc
         return img, {"primary_rays": int(stats[0]), "shadow_rays": int(stats[1]), "pixel_size": float(px[0]), "device_pixel_size": float(px[1])}
+
+    def vcm_cache_size(self, light_path_count):
+        """LightVertices::compute_cache_size of the reference (light_vertices.cpp:15-129)."""
+        return int(self.L.ref_vcm_cache_size(self.h, light_path_count))
 
     def light_emit(self, light_ids, rng_states, mis_eta_vc):
         """Light::sample_emit + initial VCM weights of the reference for (light, RNG state) pairs (ref_driver.cpp: ref_vcm_light_emit)."""

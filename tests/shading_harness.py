@@ -57,7 +57,7 @@ def compare_wave(ref_out, dev_out, tol=2e-4):
     return out
 
 
-def run_waves(scene_name, w=96, h=96, waves=4, max_path_len=10, layout="gpu", verbose=False, textured=False, envmap=False):
+def run_waves(scene_name, w=96, h=96, waves=4, max_path_len=10, layout="gpu", verbose=False, textured=False, envmap=False, phong=False):
     """Wave k feeds the REFERENCE's continuation queue of wave k-1 (traced by the oracle) to both implementations."""
     from tests.conftest import load_scene
     flat = load_scene(scene_name, layout)
@@ -68,6 +68,10 @@ def run_waves(scene_name, w=96, h=96, waves=4, max_path_len=10, layout="gpu", ve
     if textured:  # textures, bump maps and texcoords injected on the reference side, exported to the device scene
         assert rs.add_test_textures() > 0
         flat = rs.flat(scene_name)
+    if phong:     # materials that build the reference's Phong BxDF (brdfs.h:48-92), injected on the reference side
+        assert rs.add_test_phong() > 0
+        flat = rs.flat(scene_name)
+        assert (flat.arrays["materials"]["kind"] == 4).any()
     scene = api.Scene(flat)
     integ = api.Integrator(scene, api.render_settings(flat, "pt", w, h, max_path_len=max_path_len))
     xy = np.stack(np.meshgrid(np.arange(w) + 0.5, np.arange(h) + 0.5), -1).reshape(-1, 2).astype(np.float32)

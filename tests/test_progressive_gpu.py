@@ -211,3 +211,75 @@ def test_register_resident_knn_lists_equal_the_generic_search(knn, monkeypatch):
     (a, ca), (b, cb) = out
     assert ca == cb and a.sum() > 0
     assert np.abs(a - b).max() <= 1e-4 * max(1.0, a.max())
+
+
+def test_c_abi_framebuffer_allreduce_with_a_host_created_nccl_communicator():
+    """imba_integrator_allreduce: the collective of the multi-GPU path for hosts that are not Python.  The HOST creates the
+    ncclComm_t (here through ctypes on the NCCL already in the process, with one rank -- the sum over one rank is the identity);
+    the library finds ncclAllReduce in the process and reduces the integrator's framebuffer in place on the integrator's stream."""
+    import ctypes as C
+    import torch
+    from imbatracer_b200 import abi, api
+    torch.cuda.set_device(0)
+    torch.zeros(1, device="cuda")
+    import torch.cuda.nccl  # noqa: F401  (makes sure torch's NCCL is loaded)
+    nccl = None
+    for name in ("libnccl.so.2", "libnccl.so"):
+        try:
+            nccl = C.CDLL(name); break
+        except OSError:
+            continue
+    if nccl is None:
+        import glob, os
+        cands = glob.glob(os.path.join(os.path.dirname(torch.__file__), "..", "nvidia", "nccl", "lib", "libnccl.so*"))
+        assert cands, "no NCCL library found"
+        nccl = C.CDLL(cands[0], mode=C.RTLD_GLOBAL)
+
+    class UniqueId(C.Structure):
+        _fields_ = [("internal", C.c_char * 128)]
+    uid = UniqueId(); comm = C.c_void_p()
+    assert nccl.ncclGetUniqueId(C.byref(uid)) == 0
+    nccl.ncclCommInitRank.argtypes = [C.POINTER(C.c_void_p), C.c_int, UniqueId, C.c_int]
+    assert nccl.ncclCommInitRank(C.byref(comm), 1, uid, 0) == 0
+    flat = load_scene("cornell_org", "gpu")
+    sc = api.Scene(flat)
+    it = api.Integrator(sc, api.render_settings(flat, "pt", 64, 64, seed=3))
+    try:
+        it.preprocess(); it.render(2)
+        before = it.download().copy()
+        L = abi.lib()
+        L.imba_integrator_allreduce.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        abi.check(L.imba_integrator_allreduce(it.h, comm, None), "imba_integrator_allreduce")
+        after = it.download()
+        assert before.sum() > 0 and np.array_equal(before, after)
+        assert L.imba_integrator_allreduce(it.h, None, None) != 0 and "null" in abi.last_error()
+    finally:
+        it.close(); sc.close()
+        nccl.ncclCommDestroy.argtypes = [C.c_void_p]; nccl.ncclCommDestroy(comm)
+
+
+@pytest.mark.parametrize("algo", ["pt", "vcm"])
+def test_set_camera_equals_a_fresh_integrator(algo):
+    """imba_integrator_set_camera (PerspectiveCamera::move + Integrator::reset, camera.h:27-50, render_window.cpp:97-101): after the
+    move the integrator renders exactly what a new integrator created with that camera renders (same seed, schedule restarted)."""
+    import ctypes as C
+    from imbatracer_b200 import abi, api
+    flat = load_scene("cornell_org", "gpu")
+    sc = api.Scene(flat)
+    pos = (C.c_float * 3)(0.3, 1.1, 3.0); d = (C.c_float * 3)(-0.1, -0.05, -1.0); up = (C.c_float * 3)(0.0, 1.0, 0.0)
+    try:
+        a = api.Integrator(sc, api.render_settings(flat, algo, 64, 64, seed=4))
+        a.preprocess(); a.render(2); before = a.download().copy()
+        abi.check(abi.lib().imba_integrator_set_camera(a.h, pos, d, up), "set_camera")
+        a.clear(); a.render(2); moved = a.download().copy(); a.close()
+        st = api.render_settings(flat, algo, 64, 64, seed=4)
+        st.cam_pos[:] = list(pos); st.cam_dir[:] = list(d); st.cam_up[:] = list(up)
+        b = api.Integrator(sc, st)
+        b.preprocess(); b.render(2); fresh = b.download().copy(); b.close()
+        assert not np.array_equal(before, moved)
+        if algo == "pt":
+            assert np.array_equal(moved, fresh)
+        else:   # (the VCM base radius comes from preprocess(), which the moved integrator ran with the old camera, as the reference does)
+            assert abs(moved.mean() - fresh.mean()) < 0.05 * fresh.mean()
+    finally:
+        sc.close()

@@ -54,6 +54,27 @@ def test_textured_and_bump_mapped_shading_matches_reference(scene):
 
 
 @needs_ref
+@pytest.mark.parametrize("scene", ["cornell_org", "cornell_specular_front", "cornell_water"])
+def test_phong_brdf_shading_matches_reference(scene):
+    """The Phong BxDF (render/materials/brdfs.h:48-92; named by the north star, instantiated by no material of the reference's
+    loader): a material that builds BSDF(isect, Phong, nullptr) replaces the diffuse / glossy materials on the reference side
+    (oracle/ref_driver.cpp: PhongTestMaterial), the scene is exported with kind IMBA_MAT_PHONG, and both sides shade the same PT
+    wavefronts -- Phong::eval in the NEE, Phong::sample (power-cosine lobe about the mirrored direction, random draws in g++'s
+    argument order) and Phong::pdf in the MIS weights: same survivors in the same order, identical RNG states."""
+    from tests import shading_harness as sh
+    res = sh.run_waves(scene, w=96, h=96, waves=4, phong=True)
+    for r in res[1:]:
+        assert r["ref_cont"] == r["dev_cont"] and r["ref_shadow"] == r["dev_shadow"], r
+        assert r["cont_only_ref"] == 0 and r["cont_only_dev"] == 0 and r["shadow_only_ref"] == 0 and r["shadow_only_dev"] == 0, r
+        if r["ref_cont"]:
+            assert r["cont_same_order"] and r["cont_rng_equal"] == 1.0 and r["cont_flags_equal"] == 1.0, r
+            assert r["cont_close"] >= 0.998, r
+        if r["ref_shadow"]:
+            assert r["shadow_close"] >= 0.998, r
+        assert r["fb_max_abs_err"] <= 1e-4 * max(1.0, r["fb_ref_sum"]), r
+
+
+@needs_ref
 def test_environment_map_shading_matches_reference():
     """EnvMap::radiance on escaped rays (pt.cpp:95-116) and EnvLight::sample_direct as one of the NEE lights
     (light.h:443-453, 516-530): a procedural environment map is added to the reference's scene and exported."""

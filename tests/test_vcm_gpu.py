@@ -237,3 +237,55 @@ def test_reset_restarts_the_progressive_sequence():
     assert cc == ca
     assert np.abs(c - a).max() <= 1e-3 * max(1.0, a.max()) and abs(c.sum() - a.sum()) <= 2e-4 * a.sum()
     assert abs(b.sum() / 2 - a.sum() / 3) > 1e-6 * a.sum()     # not trivially equal images
+
+
+@needs_ref
+@pytest.mark.parametrize("scene", ["cornell_org", "cornell_indirect", "cornell_water", "cornell_instances", "cornell_specular_front", "stilllife_proxy"])
+def test_light_vertex_cache_size_matches_reference_probe(scene):
+    """LightVertices::compute_cache_size (light_vertices.cpp:15-129): both sides trace 10 000 probe light paths and allocate
+    margin * ceil(average number of stored vertices per path) * light_path_count slots, margin = 1.1, or 10 for fewer than 1000
+    paths (:125-126).  The average is a Monte-Carlo estimate, the ceil() makes the result an integer step function of it: the slot
+    counts must be EQUAL (the six scenes' averages lie between 2.x and 7.x, none close to an integer)."""
+    from imbatracer_b200 import abi, api
+    flat = load_scene(scene, "gpu")
+    rs = refapi.RefScene(refapi.scene_path(scene), True)
+    sc = api.Scene(flat)
+    L = abi.lib()
+    try:
+        for paths in (500, 4608, 131072):
+            want = rs.vcm_cache_size(paths)
+            for algo in ("vcm", "bpt", "ppm"):
+                it = api.Integrator(sc, api.render_settings(flat, algo, 96, 96, light_path_count=paths, seed=21))
+                it.preprocess()
+                got = L.imba_integrator_vertex_cache_size(it.h)
+                it.close()
+                assert got == want, (scene, algo, paths, got, want)
+        for algo in ("lt", "pt"):   # no cache: LT splats directly, PT has no light pass (vcm.h:78-80)
+            it = api.Integrator(sc, api.render_settings(flat, algo, 96, 96, light_path_count=4608))
+            it.preprocess()
+            assert L.imba_integrator_vertex_cache_size(it.h) == 0
+            it.close()
+    finally:
+        sc.close(); rs.close()
+
+
+@needs_ref
+@pytest.mark.parametrize("algo", ["vcm", "bpt", "lt"])
+def test_vcm_stages_with_phong_materials(algo):
+    """Phong (brdfs.h:48-92) in the bidirectional family: light-vertex storage on a glossy-reflection BSDF, connections evaluating it in
+    both directions (forward / reverse pdfs of the MIS partial weights), adjoint sampling on light paths -- same stage harness."""
+    from tests import vcm_harness as vh
+    res = vh.run("cornell_org", algo, w=64, h=64, waves=3, phong=True)
+    for r in res["light"] + res["camera"]:
+        c = r["cont"]
+        assert c["ref"] == c["dev"] and c["only_one_side"] == 0, r
+        if c["ref"]:
+            assert c["same_order"] and c["rng_equal"] == 1.0 and c["len_equal"] == 1.0 and c["close"] >= 0.998, r
+    for r in res["light"]:
+        for part in ("connect", "cache"):
+            p = r[part]
+            assert p["ref"] == p["dev"] and p["only_one_side"] <= 0.002 * max(p["ref"], 1), r
+            if p["ref"]:
+                assert p["close"] >= 0.998, r
+    for r in res["camera"]:
+        assert r["fb_rel_err"] < 2e-3, r

@@ -54,13 +54,16 @@ def compare_keyed(ra, da, key_field, fields, tol):
     return out
 
 
-def run(scene_name, algo, w=64, h=64, waves=4, iteration=3, layout="gpu", tol=5e-4, verbose=False, envmap=False, from_reference=False):
+def run(scene_name, algo, w=64, h=64, waves=4, iteration=3, layout="gpu", tol=5e-4, verbose=False, envmap=False, from_reference=False, phong=False):
     """from_reference: the scene arrays come from the reference's loader at run time (no committed fixture of that scene)."""
     from tests.conftest import load_scene
     rs = refapi.RefScene(refapi.scene_path(scene_name), layout == "gpu")
     flat = rs.flat(scene_name) if from_reference else load_scene(scene_name, layout)
     if envmap:
         assert rs.add_test_envmap() == 1
+        flat = rs.flat(scene_name)
+    if phong:   # materials that build the reference's Phong BxDF, injected on the reference side
+        assert rs.add_test_phong() > 0
         flat = rs.flat(scene_name)
     scene = api.Scene(flat)
     n_light = w * h // 2
