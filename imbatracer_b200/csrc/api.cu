@@ -30,7 +30,7 @@ static int upload(T** dst, const void* src, size_t bytes) {
 }
 
 int imba_scene_upload_accel(imba_scene* s, const Bvh8& b) {
-    if (b.max_depth + 6 > IMBA_TRAVERSAL_STACK) {
+    if (b.max_depth + 11 > IMBA_TRAVERSAL_STACK) {   // + sentinel, remainders and the five entries of the saved world-space ray
         imba_set_error("acceleration structure too deep for the traversal stack (depth %d, stack %d)", b.max_depth, IMBA_TRAVERSAL_STACK);
         return IMBA_ERR_OVERFLOW;
     }

@@ -195,6 +195,9 @@ static int pt_wavefront(imba_integrator* it, int cur, int capacity) {
     // in queue order (see pt_shade_kernel): same per-path results, 11 % less time per iteration on stilllife-proxy
     const bool sort = getenv("IMBA_PT_SORT") != nullptr;
     const int* sorted = sort ? it->part.indices : nullptr;
+    // (the sort pass resets the pixel ids of the shadow slots, which the previous wave's shadow + resolve traversal on the other
+    //  stream still reads: it has to wait for that traversal here already, not only in front of the shading kernel)
+    if (sort) IMBA_CUDA(cudaStreamWaitEvent(it->stream, it->ev_shadow_done, 0), IMBA_ERR_CUDA);
     if (sort) IMBA_CUDA(imba_sort_hits_by_material(it->part, it->hits, S.indices, S.material_count, (int*)it->shadow_states, 1, it->count[cur], 0, capacity, it->stream, false), IMBA_ERR_CUDA);
     IMBA_CUDA(imba_pt_miss(S, it->rays[cur], it->hits, (const PTState*)it->states[cur], sorted, it->part.bin_start + S.material_count, it->count[cur], capacity, it->fb, it->stream), IMBA_ERR_CUDA);
     // the previous wave's shadow traversal (other stream) reads the shadow buffers and that wave's queue count, which is this

@@ -118,6 +118,12 @@ __device__ __forceinline__ int queue_push_slot(int* count) {
     base = __shfl_sync(m, base, leader);
     return base + __popc(m & ((1u << lane) - 1u));
 }
+/* Statistics counter (TileScheduler::total_shadow_rays_, tile_scheduler.h:117-127): one atomic per converged group of lanes instead
+ * of one per ray on a single global address. */
+__device__ __forceinline__ void count_rays(unsigned long long* counter) {
+    const unsigned m = __activemask();
+    if ((int)(threadIdx.x & 31) == __ffs(m) - 1) atomicAdd(counter, (unsigned long long)__popc(m));
+}
 cudaError_t imba_pt_miss(const DeviceShading& S, const float4* rays, const int4* hits, const PTState* states, const int* sorted, const int* hit_count_ptr, const int* queue_count_ptr,
                          int capacity, float* fb, cudaStream_t st);
 cudaError_t imba_probe_raygen(const DevCamera& cam, float4* rays, int count, cudaStream_t st);

@@ -135,6 +135,13 @@ __global__ void __launch_bounds__(BLOCK_THREADS) trace_kernel(const TraceArgs P)
                     // top level: enter the instance (ray * inverse transform, cpu_adapter.cpp:356-365)
                     if (ngroup.y > 0x00ffffffu) STACK_PUSH(ngroup);
                     if (tgroup.y != 0) STACK_PUSH(tgroup);
+                    // the world-space ray (with its reciprocals and octant) goes onto the stack under the sentinel: leaving the instance
+                    // pops it back instead of reloading the ray from the queue and dividing three times again
+                    STACK_PUSH(make_uint2(__float_as_uint(r.ox), __float_as_uint(r.oy)));
+                    STACK_PUSH(make_uint2(__float_as_uint(r.oz), __float_as_uint(r.dx)));
+                    STACK_PUSH(make_uint2(__float_as_uint(r.dy), __float_as_uint(r.dz)));
+                    STACK_PUSH(make_uint2(__float_as_uint(r.ix), __float_as_uint(r.iy)));
+                    STACK_PUSH(make_uint2(__float_as_uint(r.iz), r.octinv4));
                     STACK_PUSH(make_uint2(0xffffffffu, 0u));
                     if (STATS) { st_sp = max(st_sp, (uint32_t)sp); ++st_insts; }
                     const float4* ip = P.insts + (size_t)(tgroup.x + bit) * 4;
@@ -158,9 +165,11 @@ __global__ void __launch_bounds__(BLOCK_THREADS) trace_kernel(const TraceArgs P)
                 for (;;) {
                     if (sp == 0) { done = true; break; }
                     const uint2 e = STACK_POP();
-                    if (e.y == 0u) { // sentinel: leave the instance, restore the world-space ray
-                        const float4 o = __ldg(P.rays + 2 * ray_idx), d = __ldg(P.rays + 2 * ray_idx + 1);
-                        r.ox = o.x; r.oy = o.y; r.oz = o.z; r.dx = d.x; r.dy = d.y; r.dz = d.z; r.finish();
+                    if (e.y == 0u) { // sentinel: leave the instance, restore the world-space ray saved under it
+                        const uint2 s4 = STACK_POP(), s3 = STACK_POP(), s2 = STACK_POP(), s1 = STACK_POP(), s0 = STACK_POP();
+                        r.ox = __uint_as_float(s0.x); r.oy = __uint_as_float(s0.y); r.oz = __uint_as_float(s1.x); r.dx = __uint_as_float(s1.y);
+                        r.dy = __uint_as_float(s2.x); r.dz = __uint_as_float(s2.y); r.ix = __uint_as_float(s3.x); r.iy = __uint_as_float(s3.y);
+                        r.iz = __uint_as_float(s4.x); r.octinv4 = s4.y;
                         cur_inst = -1;
                         continue;
                     }

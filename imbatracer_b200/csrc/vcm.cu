@@ -184,7 +184,7 @@ __global__ void __launch_bounds__(128) vcm_light_shade_kernel(const DeviceShadin
     const bool alive = light_vertex<ALGO>(S, P, cam, ro, rd, hits[idx], st, cache, cache_capacity, cache_last, has_shadow, sh_o, sh_d, ss);
     if (has_shadow) {
         shadow_rays[2 * idx] = sh_o; shadow_rays[2 * idx + 1] = sh_d; shadow_states[idx] = ss;
-        if (ray_stats) atomicAdd(ray_stats + 1, 1ull);
+        if (ray_stats) count_rays(ray_stats + 1);
     }
     if (alive) {
         const int o = out_count ? queue_push_slot(out_count) : idx;
@@ -588,7 +588,7 @@ __global__ void __launch_bounds__(128) vcm_camera_shade_kernel(const DeviceShadi
             shadow_rays[2 * slot + 1] = make_float4(s.dir.x, s.dir.y, s.dir.z, s.distance - off);
             ShadowState ss; ss.pixel_id = st.pixel_id; ss.r = c.x; ss.g = c.y; ss.b = c.z;
             shadow_states[slot] = ss;
-            if (ray_stats) atomicAdd(ray_stats + 1, 1ull);
+            if (ray_stats) count_rays(ray_stats + 1);
         }
     }
     const GridParams g = *gp; // g.count = number of cached light vertices of this iteration
@@ -624,7 +624,7 @@ __global__ void __launch_bounds__(128) vcm_camera_shade_kernel(const DeviceShadi
             shadow_rays[2 * slot + 1] = make_float4(connect_dir.x, connect_dir.y, connect_dir.z, dist - off);
             ShadowState ss; ss.pixel_id = st.pixel_id; ss.r = cc.x; ss.g = cc.y; ss.b = cc.z;
             shadow_states[slot] = ss;
-            if (ray_stats) atomicAdd(ray_stats + 1, 1ull);
+            if (ray_stats) count_rays(ray_stats + 1);
         }
     }
     if (ALGO != IMBA_ALGO_BPT && ALGO != IMBA_ALGO_VCM_PT && !bsdf.is_specular()) { // vertex_merging (vcm.cpp:572-611)

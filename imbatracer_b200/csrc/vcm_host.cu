@@ -53,9 +53,10 @@ static int vcm_wavefront(imba_integrator* it, int algo, bool light, int cur, int
     if (rc != IMBA_OK) return rc;
     // IMBA_VCM_SORT=1: the reference's order of work (compact_hits + sort_by_material, vcm.cpp:197-210, 327-340); default: queue order
     const bool sort = getenv("IMBA_VCM_SORT") != nullptr;
-    if (sort) IMBA_CUDA(imba_sort_hits_by_material(it->part, it->hits, S.indices, S.material_count, (int*)it->shadow_states, slots, it->count[cur], 0, capacity, it->stream, false), IMBA_ERR_CUDA);
-    // (camera pass) the previous wave's shadow traversal on the second stream still reads the shadow buffers and its queue count
+    // the previous wave's shadow traversal on the second stream still reads the shadow buffers and its queue count; the sort pass
+    // already rewrites the pixel ids of the shadow slots, so the wait comes in front of it
     if (overlap_shadows) IMBA_CUDA(cudaStreamWaitEvent(it->stream, it->ev_shadow_done, 0), IMBA_ERR_CUDA);
+    if (sort) IMBA_CUDA(imba_sort_hits_by_material(it->part, it->hits, S.indices, S.material_count, (int*)it->shadow_states, slots, it->count[cur], 0, capacity, it->stream, false), IMBA_ERR_CUDA);
     IMBA_CUDA(cudaMemsetAsync(it->count[cur ^ 1], 0, sizeof(int), it->stream), IMBA_ERR_CUDA);
     const VcmLaunch a = base_launch(it, cur, capacity, sort);
     IMBA_CUDA(light ? imba_vcm_light_shade(algo, a, it->stream) : imba_vcm_camera_shade(algo, a, it->stream), IMBA_ERR_CUDA);

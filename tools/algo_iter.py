@@ -3,7 +3,9 @@
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench
-from imbatracer_b200 import api
+from imbatracer_b200 import api, abi
+if os.environ.get('IMBA_LIB_VARIANT'):
+    abi.LIB_PATH = os.path.join(os.path.dirname(abi.LIB_PATH), os.environ['IMBA_LIB_VARIANT'])
 algo = sys.argv[1]; iters = int(sys.argv[2]) if len(sys.argv) > 2 else 2
 flat = bench.load_flat(); scene = api.Scene(flat, device_build=True)
 it = api.Integrator(scene, api.render_settings(flat, algo, 1920, 1080, seed=5))
