@@ -496,6 +496,27 @@ def host_copy_bandwidth(barrier, mib=256, reps=4):
     return 2 * a.nbytes * reps / (time.perf_counter() - t0) / 1e9
 
 
+def raw_pcie_bandwidth(barrier, mib=256, reps=4):
+    """What the host can feed: plain cudaMemcpyAsync of pinned buffers, host->device and device->host at the same time on two
+    streams, all ranks at once (GB/s of this rank, both directions added).  The host-queue path cannot beat the sum over ranks."""
+    import torch
+    n = mib << 18
+    h_up = torch.empty(n, dtype=torch.float32).pin_memory(); h_dn = torch.empty(n // 2, dtype=torch.float32).pin_memory()   # 2 : 1 like rays : hits
+    d_up = torch.empty(n, dtype=torch.float32, device="cuda"); d_dn = torch.empty(n // 2, dtype=torch.float32, device="cuda")
+    s_up, s_dn = torch.cuda.Stream(), torch.cuda.Stream()
+    def go():
+        with torch.cuda.stream(s_up):
+            d_up.copy_(h_up, non_blocking=True)
+        with torch.cuda.stream(s_dn):
+            h_dn.copy_(d_dn, non_blocking=True)
+    go(); torch.cuda.synchronize(); barrier()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        go()
+    torch.cuda.synchronize()
+    return (h_up.nbytes + h_dn.nbytes) * reps / (time.perf_counter() - t0) / 1e9
+
+
 def run_ours(args):
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
     binding = bind_to_gpu_numa_node(local) if world > 1 and not os.environ.get("IMBA_BENCH_NO_BIND") else "single rank: not bound"
@@ -570,6 +591,7 @@ def run_ours(args):
     barrier()
     e2e_s = time.perf_counter() - t0
     host_bw = host_copy_bandwidth(barrier) if world > 1 else 0.0
+    raw_pcie = raw_pcie_bandwidth(barrier)
     # configs[2] AS STATED: PT 1920x1080, 256 spp IN TOTAL split over the ranks (strong scaling), one NCCL sum of the float framebuffer
     # per step.  8 progressive iterations per wavefront pass (imba_render_settings::iterations_per_pass) and per sum; every path keeps
     # the seed of its own iteration, the image is that of single passes -- which `pt_single_pass` times for comparison
@@ -583,7 +605,7 @@ def run_ours(args):
     sampler.stop_flag = True; sampler.join(timeout=2)
 
     t = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
-    bw = torch.tensor([host_bw], dtype=torch.float64, device="cuda")
+    bw = torch.tensor([host_bw, raw_pcie], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(bw, op=dist.ReduceOp.SUM)
@@ -639,7 +661,10 @@ def run_ours(args):
                 "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": 4 * n * 32, "d2h_bytes_per_step": 4 * n * 16,
                         "steps": e2e_steps, "note": "imba_trace_host on pinned host queues from 4 host threads (one per queue), wall clock",
                         "pcie_gb_s_per_gpu": e2e_value * 1e6 * 48 / 1e9 / world, "host_cores": os.cpu_count(), "cpu_binding_rank0": binding,
-                        "host_copy_gb_s_all_ranks": float(bw[0]) if world > 1 else None},
+                        "host_copy_gb_s_all_ranks": float(bw[0]) if world > 1 else None,
+                        "raw_memcpy_gb_s_all_ranks": float(bw[1]),
+                        "limit_note": "pcie_gb_s_per_gpu x n_gpus against raw_memcpy_gb_s_all_ranks (pinned cudaMemcpyAsync up and down at once on every rank, no kernels): "
+                                      "what the host's memory / PCIe complex delivers to all GPUs together bounds this path, not the traversal"},
                 "gpu_launches": int(launches),
                 "clocks": sampler.summary(),
                 "parity_sample": parity_sample(flat, scene, batches),
