@@ -21,7 +21,7 @@
 #include "vecmath.cuh"
 
 enum { BSDF_NONE = 0, BSDF_REFLECTION = 1, BSDF_TRANSMISSION = 2, BSDF_DIFFUSE = 4, BSDF_GLOSSY = 8, BSDF_SPECULAR = 16 };
-enum { MAT_DIFFUSE = 0, MAT_MIRROR = 1, MAT_GLASS = 2, MAT_GLOSSY = 3, MAT_PHONG = 4 };
+enum { MAT_DIFFUSE = 0, MAT_MIRROR = 1, MAT_GLASS = 2, MAT_GLOSSY = 3, MAT_PHONG = 4, MAT_OREN_NAYAR = 5 };
 enum { LIGHT_TRIANGLE = 0, LIGHT_DIRECTIONAL = 1, LIGHT_POINT = 2, LIGHT_SPOT = 3, LIGHT_ENV = 4 };
 
 struct DevLight {            // 7 x float4
@@ -167,7 +167,7 @@ struct Bsdf {
     __device__ __forceinline__ bool has_btdf() const { return kind == MAT_GLASS; }
     __device__ __forceinline__ bool is_specular() const { return kind == MAT_MIRROR || kind == MAT_GLASS; } // Material::is_specular
     __device__ __forceinline__ int brdf_flags() const {
-        return kind == MAT_DIFFUSE ? (BSDF_DIFFUSE | BSDF_REFLECTION)
+        return (kind == MAT_DIFFUSE || kind == MAT_OREN_NAYAR) ? (BSDF_DIFFUSE | BSDF_REFLECTION)
              : kind == MAT_GLOSSY  ? (BSDF_GLOSSY | BSDF_DIFFUSE | BSDF_REFLECTION)
              : kind == MAT_PHONG   ? (BSDF_GLOSSY | BSDF_REFLECTION) : (BSDF_SPECULAR | BSDF_REFLECTION);
     }
@@ -214,16 +214,35 @@ struct Bsdf {
         return (exponent + 1.0f) * powf(fabsf(h.z), exponent) / (2.0f * IMBA_PI * 4.0f * dot(o, h));
     }
     __device__ __forceinline__ V3 lambert_eval(V3 o, V3 i) const { return o.z * i.z > 0.0f ? kd * (1.0f / IMBA_PI) : v3(0.0f); }
+    // OrenNayar (brdfs.h:94-134): reflectance kd, roughness sigma (degrees) in `exponent`; sample / pdf are BxDF's cosine-hemisphere defaults
+    static __device__ __forceinline__ float on_sin_theta(V3 d) { return sqrtf(fmaxf(0.0f, 1.0f - sqr(d.z))); }
+    static __device__ __forceinline__ float on_cos_phi(V3 d) { const float st = on_sin_theta(d); return st == 0.0f ? 1.0f : fminf(fmaxf(d.x / st, -1.0f), 1.0f); }
+    static __device__ __forceinline__ float on_sin_phi(V3 d) { const float st = on_sin_theta(d); return st == 0.0f ? 0.0f : fminf(fmaxf(d.y / st, -1.0f), 1.0f); }
+    __device__ __forceinline__ V3 oren_nayar_eval(V3 o, V3 i) const {
+        const float sigma = exponent * IMBA_PI / 180.0f;
+        const float sigma_sqr = sigma * sigma;
+        const float pa = 1.0f - sigma_sqr / (2.0f * (sigma_sqr + 0.33f));
+        const float pb = (float)(0.45 * (double)sigma_sqr / (double)(sigma_sqr + 0.09f));   // `0.45 * ...` is a double expression in the reference
+        const float sin_theta_in = on_sin_theta(i), sin_theta_out = on_sin_theta(o);
+        float max_cos = 0.0f;
+        if (sin_theta_in > 0.0001f && sin_theta_out > 0.0001f)
+            max_cos = fmaxf(0.0f, on_cos_phi(i) * on_cos_phi(o) + on_sin_phi(i) * on_sin_phi(o));
+        float sin_alpha, tan_beta;
+        if (fabsf(i.z) > fabsf(o.z)) { sin_alpha = sin_theta_out; tan_beta = sin_theta_in / fabsf(i.z); }
+        else                         { sin_alpha = sin_theta_in;  tan_beta = sin_theta_out / fabsf(o.z); }
+        return o.z * i.z > 0.0f ? kd * (1.0f / IMBA_PI) * (pa + pb * max_cos * sin_alpha * tan_beta) : v3(0.0f);
+    }
     __device__ __forceinline__ float lambert_pdf(V3 o, V3 i) const { return o.z * i.z > 0.0f ? fabsf(i.z) / IMBA_PI : 0.0f; }
 
     __device__ __forceinline__ V3 brdf_eval(V3 o, V3 i) const {
         if (kind == MAT_DIFFUSE) return lambert_eval(o, i);
         if (kind == MAT_GLOSSY) return 0.5f * (cook_eval(o, i) + lambert_eval(o, i));
         if (kind == MAT_PHONG) return phong_eval(o, i);
+        if (kind == MAT_OREN_NAYAR) return oren_nayar_eval(o, i);
         return v3(0.0f);
     }
     __device__ __forceinline__ float brdf_pdf(V3 o, V3 i) const {
-        if (kind == MAT_DIFFUSE) return lambert_pdf(o, i);
+        if (kind == MAT_DIFFUSE || kind == MAT_OREN_NAYAR) return lambert_pdf(o, i);
         if (kind == MAT_GLOSSY) return (cook_pdf(o, i) + lambert_pdf(o, i)) * 0.5f;
         if (kind == MAT_PHONG) return phong_pdf(o, i);
         return 0.0f;
@@ -243,7 +262,7 @@ struct Bsdf {
         i = v3(st * cosf(phi), st * sinf(phi), ct);
         pdf_out = i.z / IMBA_PI;
         if (o.z < 0.0f) i.z = -i.z;
-        return lambert_eval(o, i);
+        return kind == MAT_OREN_NAYAR ? oren_nayar_eval(o, i) : lambert_eval(o, i);
     }
     __device__ __forceinline__ V3 cook_sample(V3 o, V3& i, Rng& rng, float& pdf_out) const {
         const float r2 = rng.uniform(), r1 = rng.uniform();
@@ -258,7 +277,7 @@ struct Bsdf {
         return o.z * i.z > 0.0f ? cook_eval(o, i) : v3(0.0f);
     }
     __device__ __forceinline__ V3 brdf_sample(V3 o, V3& i, Rng& rng, float& pdf_out) const {
-        if (kind == MAT_DIFFUSE) return lambert_sample(o, i, rng, pdf_out);
+        if (kind == MAT_DIFFUSE || kind == MAT_OREN_NAYAR) return lambert_sample(o, i, rng, pdf_out);
         if (kind == MAT_GLOSSY) return rng.uniform() < 0.5f ? cook_sample(o, i, rng, pdf_out) : lambert_sample(o, i, rng, pdf_out);
         if (kind == MAT_PHONG) return phong_sample(o, i, rng, pdf_out);
         // SpecularReflection (brdfs.h:25-45): conductor fresnel for mirrors, dielectric(1, eta) for glass
@@ -287,7 +306,7 @@ struct Bsdf {
     /* bsdf.h:149-204 with flags = BSDF_ALL, or (specular_only) SPECULAR | REFLECTION | TRANSMISSION as the PPM camera
      * pass requests (vcm.cpp:141-143): non-specular BRDFs then do not match and nothing is drawn from the RNG */
     __device__ __forceinline__ V3 sample(V3 out_dir, V3& in_dir, Rng& rng, int& sampled_flags, float& pdf_out, bool specular_only = false) const {
-        if (specular_only && (kind == MAT_DIFFUSE || kind == MAT_GLOSSY || kind == MAT_PHONG)) { pdf_out = 0.0f; sampled_flags = 0; return v3(0.0f); }
+        if (specular_only && (kind == MAT_DIFFUSE || kind == MAT_GLOSSY || kind == MAT_PHONG || kind == MAT_OREN_NAYAR)) { pdf_out = 0.0f; sampled_flags = 0; return v3(0.0f); }
         const V3 lo = to_local(out_dir);
         const float btdf_prob = has_btdf() ? 1.0f - fresnel_dielectric_eval(lo.z, 1.0f, eta) : 0.0f;
         const float rnd = rng.uniform();

@@ -102,8 +102,9 @@ typedef enum { IMBA_ACCEL_MBVH4 = 0, IMBA_ACCEL_BVH2 = 1,
                 * replaces SplitBvhBuilder (core/sbvh_builder.h) + the adapters for scenes loaded without one */
                IMBA_ACCEL_DEVICE_BUILD = 2 } imba_accel_layout;
 /* IMBA_MAT_PHONG: a BSDF holding the reference's Phong BxDF (render/materials/brdfs.h:48-92; coefficient = ks, exponent).  No material of
- * the reference's loader instantiates it (build_scene.cpp:125-161), a host program that does builds BSDF(isect, Phong, nullptr). */
-typedef enum { IMBA_MAT_DIFFUSE = 0, IMBA_MAT_MIRROR = 1, IMBA_MAT_GLASS = 2, IMBA_MAT_GLOSSY = 3, IMBA_MAT_PHONG = 4 } imba_material_kind;
+ * the reference's loader instantiates it (build_scene.cpp:125-161), a host program that does builds BSDF(isect, Phong, nullptr).
+ * IMBA_MAT_OREN_NAYAR: likewise for OrenNayar (brdfs.h:94-134; reflectance = kd, roughness in degrees = exponent field). */
+typedef enum { IMBA_MAT_DIFFUSE = 0, IMBA_MAT_MIRROR = 1, IMBA_MAT_GLASS = 2, IMBA_MAT_GLOSSY = 3, IMBA_MAT_PHONG = 4, IMBA_MAT_OREN_NAYAR = 5 } imba_material_kind;
 typedef enum { IMBA_LIGHT_TRIANGLE = 0, IMBA_LIGHT_DIRECTIONAL = 1, IMBA_LIGHT_POINT = 2, IMBA_LIGHT_SPOT = 3,
                IMBA_LIGHT_ENV = 4 } imba_light_kind;
 

@@ -78,6 +78,17 @@ public:
     }
     rgb coefficient_; float exponent_;
 };
+// ... and for OrenNayar (brdfs.h:94-134), equally never instantiated by the reference's materials
+class OrenNayarTestMaterial : public Material {
+public:
+    OrenNayarTestMaterial(const rgb& reflectance, float roughness_degrees) : reflectance_(reflectance), roughness_(roughness_degrees) {}
+    Material* duplicate() const override final { return new OrenNayarTestMaterial(reflectance_, roughness_); }
+    BSDF* get_bsdf(const Intersection& isect, MemoryArena& mem_arena, bool adjoint) const override {
+        auto brdf = mem_arena.alloc<OrenNayar>(reflectance_, roughness_);
+        return mem_arena.alloc<BSDF>(isect, brdf, nullptr);
+    }
+    rgb reflectance_; float roughness_;
+};
 
 
 namespace {
@@ -303,6 +314,9 @@ int ref_scene_export(void* h, imba_scene_desc* d) {
             o.kind = IMBA_MAT_GLASS; o.eta = p->eta_;
             o.ks[0] = p->reflectance_.x; o.ks[1] = p->reflectance_.y; o.ks[2] = p->reflectance_.z;
             o.tf[0] = p->transmittance_.x; o.tf[1] = p->transmittance_.y; o.tf[2] = p->transmittance_.z;
+        } else if (auto p = dynamic_cast<OrenNayarTestMaterial*>(mat)) {
+            o.kind = IMBA_MAT_OREN_NAYAR; o.exponent = p->roughness_;
+            o.kd[0] = p->reflectance_.x; o.kd[1] = p->reflectance_.y; o.kd[2] = p->reflectance_.z;
         } else if (auto p = dynamic_cast<PhongTestMaterial*>(mat)) {
             o.kind = IMBA_MAT_PHONG; o.exponent = p->exponent_;
             o.ks[0] = p->coefficient_.x; o.ks[1] = p->coefficient_.y; o.ks[2] = p->coefficient_.z;
@@ -633,7 +647,8 @@ int ref_scene_add_test_textures(void* h, uint64_t seed) {
     return changed;
 }
 
-/// Replaces every non-emissive diffuse / glossy material by a PhongTestMaterial (coefficient from its colour, exponent 4 .. 67).
+/// Replaces the non-emissive diffuse / glossy materials alternately by a PhongTestMaterial (coefficient from its colour, exponent
+/// 4 .. 67) and an OrenNayarTestMaterial (reflectance from its colour, roughness 5 .. 44 degrees).
 int ref_scene_add_test_phong(void* h, uint64_t seed) {
     auto rs = (RefScene*)h; Scene& sc = *rs->scene;
     RNG rng(seed);
@@ -645,7 +660,10 @@ int ref_scene_add_test_phong(void* h, uint64_t seed) {
         if (auto d = dynamic_cast<DiffuseMaterial*>(mat)) c = d->sampler_ ? rgb(0.6f, 0.5f, 0.4f) : d->color_;
         else if (auto g = dynamic_cast<GlossyMaterial*>(mat)) c = g->specular_color_;
         else continue;
-        sc.materials()[m].reset(new PhongTestMaterial(0.25f * c + rgb(0.05f), 4.0f + floorf(64.0f * rng.random_float()))); ++changed;
+        const float r = rng.random_float();
+        if (m % 2 == 0) sc.materials()[m].reset(new PhongTestMaterial(0.25f * c + rgb(0.05f), 4.0f + floorf(64.0f * r)));
+        else            sc.materials()[m].reset(new OrenNayarTestMaterial(0.8f * c + rgb(0.05f), 5.0f + floorf(40.0f * r)));
+        ++changed;
     }
     return changed;
 }

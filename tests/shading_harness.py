@@ -71,7 +71,7 @@ def run_waves(scene_name, w=96, h=96, waves=4, max_path_len=10, layout="gpu", ve
     if phong:     # materials that build the reference's Phong BxDF (brdfs.h:48-92), injected on the reference side
         assert rs.add_test_phong() > 0
         flat = rs.flat(scene_name)
-        assert (flat.arrays["materials"]["kind"] == 4).any()
+        assert (flat.arrays["materials"]["kind"] == 4).any() and (flat.arrays["materials"]["kind"] == 5).any()   # Phong and OrenNayar
     scene = api.Scene(flat)
     integ = api.Integrator(scene, api.render_settings(flat, "pt", w, h, max_path_len=max_path_len))
     xy = np.stack(np.meshgrid(np.arange(w) + 0.5, np.arange(h) + 0.5), -1).reshape(-1, 2).astype(np.float32)

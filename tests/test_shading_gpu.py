@@ -56,9 +56,10 @@ def test_textured_and_bump_mapped_shading_matches_reference(scene):
 @needs_ref
 @pytest.mark.parametrize("scene", ["cornell_org", "cornell_specular_front", "cornell_water"])
 def test_phong_brdf_shading_matches_reference(scene):
-    """The Phong BxDF (render/materials/brdfs.h:48-92; named by the north star, instantiated by no material of the reference's
-    loader): a material that builds BSDF(isect, Phong, nullptr) replaces the diffuse / glossy materials on the reference side
-    (oracle/ref_driver.cpp: PhongTestMaterial), the scene is exported with kind IMBA_MAT_PHONG, and both sides shade the same PT
+    """The Phong BxDF (render/materials/brdfs.h:48-92; named by the north star) and OrenNayar (brdfs.h:94-134), both instantiated by no
+    material of the reference's loader: materials that build BSDF(isect, Phong, nullptr) / BSDF(isect, OrenNayar, nullptr) replace the
+    diffuse / glossy materials alternately on the reference side (oracle/ref_driver.cpp: PhongTestMaterial, OrenNayarTestMaterial), the
+    scene is exported with kinds IMBA_MAT_PHONG / IMBA_MAT_OREN_NAYAR, and both sides shade the same PT
     wavefronts -- Phong::eval in the NEE, Phong::sample (power-cosine lobe about the mirrored direction, random draws in g++'s
     argument order) and Phong::pdf in the MIS weights: same survivors in the same order, identical RNG states."""
     from tests import shading_harness as sh
