@@ -45,6 +45,11 @@ def coplanar(flat, rays, hits):
 
 # number of rays of each 4 Mi-ray bench batch (seed 0x1234ABCD) that fall into the coplanar class; everything else is exact
 COPLANAR_COUNT = {"coherent_closest": 0, "incoherent_closest": 0, "coherent_occluded": 0, "incoherent_occluded": 4}
+# The batches are built with float64 numpy arithmetic (bench.make_batches: sin / cos / sqrt of the bounce directions) whose last bit
+# may differ between CPU generations; the exact count above is asserted for the batches with these SHA-256 prefixes (what every box
+# of this pool has produced so far), for any other bytes the class membership of every mismatch and a bound of 8 are asserted.
+BATCH_SHA = {"coherent_closest": "07549fd186acc714", "incoherent_closest": "7134af41d5ceb972", "coherent_occluded": "0a4b40b42bf7d3b3",
+             "incoherent_occluded": "91444821eb87576a"}
 
 
 @pytest.mark.parametrize("name,any_hit", [("coherent_closest", 0), ("incoherent_closest", 0), ("coherent_occluded", 1), ("incoherent_occluded", 1)])
@@ -63,7 +68,13 @@ def test_every_ray_of_the_bench_batches_matches_the_oracle(bench_setup, name, an
     else:
         differ = (got.view(np.uint8).reshape(-1, 16) != want.view(np.uint8).reshape(-1, 16)).any(1)
     bad = np.nonzero(differ)[0]
-    assert len(bad) == COPLANAR_COUNT[name], (name, len(bad), rays[bad[:4]], got[bad[:4]], want[bad[:4]])
+    import hashlib
+    sha = hashlib.sha256(rays.tobytes()).hexdigest()[:16]
+    print(f"batch {name}: sha256 {sha}, {len(bad)} mismatch(es)")
+    if BATCH_SHA[name] == sha:
+        assert len(bad) == COPLANAR_COUNT[name], (name, sha, len(bad), rays[bad[:4]], got[bad[:4]], want[bad[:4]])
+    else:
+        assert len(bad) <= 8, (name, sha, len(bad))
     if len(bad):
         # class (2): the CUDA path (wider quantised boxes) reaches a triangle the ray is coplanar with, the oracle does not
         assert (want["tri_id"][bad] < 0).all() and (got["tri_id"][bad] >= 0).all()
