@@ -12,6 +12,7 @@
  */
 #include <cstdio>
 #include <cstring>
+#include <new>
 #include <string>
 #include <vector>
 #include "api_common.h"
@@ -32,7 +33,9 @@ extern "C" imba_bvh_file* imba_bvh_cache_open(const char* path) {
     if (!in) { imba_set_error("cannot open %s", path ? path : "(null)"); return nullptr; }
     uint32_t magic = 0;
     if (fread(&magic, 4, 1, in) != 1 || magic != MAGIC) { fclose(in); imba_set_error("%s is not a .bvh cache (bad magic)", path); return nullptr; }
+    fseek(in, 0, SEEK_END); const uint64_t file_size = (uint64_t)ftell(in); fseek(in, 4, SEEK_SET);
     imba_bvh_file* f = new imba_bvh_file;
+    try {
     for (;;) {
         uint64_t size = 0; uint32_t type = 0;
         if (fread(&size, 8, 1, in) != 1) break;
@@ -46,6 +49,7 @@ extern "C" imba_bvh_file* imba_bvh_cache_open(const char* path) {
         b.node_count = h[0]; b.prim_count = h[1];
         const uint64_t want = 8 + (uint64_t)nb * h[0] + (uint64_t)prim_bytes(type) * h[1];
         if (want != payload) { imba_set_error("block of type %u in %s has inconsistent size", type, path); delete f; fclose(in); return nullptr; }
+        if (payload > file_size) { imba_set_error("block of type %u in %s is larger than the file", type, path); delete f; fclose(in); return nullptr; }   // untrusted counts never size an allocation beyond the file
         b.nodes.resize(nb * h[0]); b.prims.resize(prim_bytes(type) * h[1]);
         if ((b.nodes.size() && fread(b.nodes.data(), 1, b.nodes.size(), in) != b.nodes.size()) ||
             (b.prims.size() && fread(b.prims.data(), 1, b.prims.size(), in) != b.prims.size())) {
@@ -53,8 +57,30 @@ extern "C" imba_bvh_file* imba_bvh_cache_open(const char* path) {
         }
         f->blocks.push_back(std::move(b));
     }
+    } catch (const std::bad_alloc&) {   // no exception crosses the C ABI
+        imba_set_error("out of memory reading %s", path); delete f; fclose(in); return nullptr;
+    }
     fclose(in);
     return f;
+}
+
+/* What the reference's store_accel_* looks at before appending (load_bvh.cpp:144-157): the magic, and the block headers for a
+ * block of the same type -- without loading or validating any payload.  Returns -1 no such file, -2 not a .bvh cache, 1 a block of
+ * `type` is present, 0 otherwise. */
+static int scan_headers(const char* path, uint32_t type) {
+    FILE* in = fopen(path, "rb");
+    if (!in) return -1;
+    uint32_t magic = 0;
+    if (fread(&magic, 4, 1, in) != 1 || magic != MAGIC) { fclose(in); return -2; }
+    int found = 0;
+    for (;;) {
+        uint64_t size = 0; uint32_t t = 0;
+        if (fread(&size, 8, 1, in) != 1 || fread(&t, 4, 1, in) != 1 || size < 4) break;   // end of file or a damaged tail: stop scanning
+        if (t == type) { found = 1; break; }
+        if (fseek(in, (long)(size - 4), SEEK_CUR) != 0) break;
+    }
+    fclose(in);
+    return found;
 }
 
 extern "C" int imba_bvh_cache_block(const imba_bvh_file* f, int type, const void** nodes, uint32_t* node_count, const void** prims, uint32_t* prim_count) {
@@ -75,14 +101,12 @@ extern "C" int imba_bvh_cache_block(const imba_bvh_file* f, int type, const void
 extern "C" int imba_bvh_cache_append(const char* path, int type, const void* nodes, uint32_t node_count, const void* prims, uint32_t prim_count) {
     const size_t nb = node_bytes((uint32_t)type);
     if (!path || nb == 0 || (node_count && !nodes) || (prim_count && !prims)) { imba_set_error("invalid argument"); return IMBA_ERR_INVALID; }
-    bool exists = false;
-    if (imba_bvh_file* f = imba_bvh_cache_open(path)) {
-        exists = true;
-        bool dup = false;
-        for (const Block& b : f->blocks) dup = dup || (int)b.type == type;
-        imba_bvh_cache_close(f);
-        if (dup) { imba_set_error("%s already contains a block of type %d", path, type); return IMBA_ERR_INVALID; }
-    }
+    // existence is decided from the magic alone, as the reference does: a file whose later blocks are damaged is appended to, never
+    // truncated (its good blocks -- e.g. the BVH the reference's own loader cached -- stay); a file that is not a cache is refused
+    const int state = scan_headers(path, (uint32_t)type);
+    if (state == -2) { imba_set_error("%s exists and is not a .bvh cache: not overwritten", path); return IMBA_ERR_INVALID; }
+    if (state == 1) { imba_set_error("%s already contains a block of type %d", path, type); return IMBA_ERR_INVALID; }
+    const bool exists = state >= 0;
     FILE* out = fopen(path, exists ? "ab" : "wb");
     if (!out) { imba_set_error("cannot write %s", path); return IMBA_ERR_INVALID; }
     if (!exists) fwrite(&MAGIC, 4, 1, out);

@@ -143,14 +143,17 @@ static int light_pass(imba_integrator* it, int algo, const PtSeeds& seeds, int p
             break;
         }
         const int tail_rays = std::min(TAIL_RAYS, it->capacity);
-        if (use_graph && n <= tail_rays && cur == 0) {
+        // the captured wavefront graph holds the cache / parameter pointers of ONE buffer set: it is only used when the iterations are
+        // not pipelined over two sets (IMBA_VCM_NO_PIPELINE, or integrators without a second set)
+        const bool two_sets = it->vset[1].cache != nullptr && !getenv("IMBA_VCM_NO_PIPELINE") && !getenv("IMBA_VCM_SORT");
+        if (use_graph && !two_sets && n <= tail_rays && cur == 0) {
             IMBA_CUDA(cudaStreamWaitEvent(it->stream, it->ev_shadow_done, 0), IMBA_ERR_CUDA);
             if (!it->tail_graph) { const int rc = build_tail_graph(it, algo); if (rc != IMBA_OK) return rc; }
             IMBA_CUDA(cudaGraphLaunch(it->tail_graph, it->stream), IMBA_ERR_CUDA);
             g_imba_launches.fetch_add(TAIL_WAVES * 6);
             w += TAIL_WAVES; // an even number of wavefronts: the live queue is queue 0 again
         } else {
-            const int k_end = (use_graph && n <= tail_rays) ? 1 : batch; // make the parity even before switching to the graph
+            const int k_end = (use_graph && !two_sets && n <= tail_rays) ? 1 : batch; // make the parity even before switching to the graph
             for (int k = 0; k < k_end; ++k, cur ^= 1, ++w) {
                 const int rc = vcm_wavefront(it, algo, true, cur, n, true);   // camera-connection shadow rays beside the next wave's traversal
                 if (rc != IMBA_OK) return rc;
@@ -309,7 +312,16 @@ static void grid_stats(imba_integrator* it) { // occupancy of the photon hash gr
  * warp each, latency-bound for ~10 ms at 1080p: vcm.cu) on a side stream.  What a camera pass reads is double-buffered; when
  * the call returns no camera pass is pending.  IMBA_VCM_NO_PIPELINE=1 (and the sorted order, which shares its scratch
  * buffers) runs the passes strictly one after the other as the reference does. */
+static int vcm_render_iterations(imba_integrator* it, int iterations);
 int imba_vcm_render(imba_integrator* it, int iterations) {
+    const int rc = vcm_render_iterations(it, iterations);
+    if (rc != IMBA_OK) {   // leave no half-finished pipeline behind: no pending camera pass, light-pass queues and set 0 current
+        it->camera_pending = false;
+        if (it->cache_last) { use_set(it, 0); use_queues(it, it->light_q); }
+    }
+    return rc;
+}
+static int vcm_render_iterations(imba_integrator* it, int iterations) {
     if (!it->cache_last) { imba_set_error("imba_integrator_preprocess must be called before rendering with a VCM-family integrator"); return IMBA_ERR_INVALID; }
     const int algo = it->cfg.algorithm;
     const bool pipelined = it->vset[1].cache != nullptr && !getenv("IMBA_VCM_NO_PIPELINE") && !getenv("IMBA_VCM_SORT");

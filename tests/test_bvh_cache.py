@@ -59,3 +59,29 @@ def test_new_block_type_roundtrip_and_duplicate_refusal(tmp_path):
     assert open(fresh, "rb").read(4) == (0x313F1A57).to_bytes(4, "little")
     bad = str(tmp_path / "bad.bvh"); open(bad, "wb").write(b"not a cache")
     assert not L.imba_bvh_cache_open(bad.encode()) and "magic" in abi.last_error()
+
+
+def test_append_never_destroys_an_existing_cache(tmp_path):
+    """A cache whose LATER block is damaged still holds the good blocks the reference's loader wrote: appending decides "exists" from
+    the magic alone, like store_accel_* (load_bvh.cpp:144-157), and appends -- it must not reopen the file for writing.  A file that
+    is not a cache at all is refused, not overwritten; header counts larger than the file never size an allocation."""
+    src = os.path.join(GOLDEN, "CornellBox-Original.bvh")
+    good = open(src, "rb").read()
+    L = abi.lib()
+    b8 = refapi.Bvh8Host(load_scene("cornell_org", "gpu"))
+    # good reference blocks followed by a block header that claims more payload than there is (a torn write)
+    torn = str(tmp_path / "torn.bvh")
+    open(torn, "wb").write(good + (1 << 20).to_bytes(8, "little") + (2).to_bytes(4, "little") + b"\x01\x02\x03")
+    assert not L.imba_bvh_cache_open(torn.encode())                       # the strict reader refuses the file ...
+    abi.check(L.imba_bvh_cache_append(torn.encode(), 3, b8.nodes.ctypes.data, len(b8.nodes), b8.tris.ctypes.data, len(b8.tris)))
+    assert open(torn, "rb").read()[:len(good)] == good                   # ... but the append kept every byte that was there
+    # not a cache: refused, untouched
+    other = str(tmp_path / "notes.txt"); open(other, "wb").write(b"important, not a cache")
+    assert L.imba_bvh_cache_append(other.encode(), 3, b8.nodes.ctypes.data, len(b8.nodes), b8.tris.ctypes.data, len(b8.tris)) != 0
+    assert open(other, "rb").read() == b"important, not a cache"
+    # absurd counts in a header: error, not an allocation of 4 G nodes
+    huge = str(tmp_path / "huge.bvh")
+    payload = 8 + 56 * 0xFFFFFFF0 + 16 * 0xFFFFFFF0
+    open(huge, "wb").write((0x313F1A57).to_bytes(4, "little") + (payload + 4).to_bytes(8, "little") + (1).to_bytes(4, "little") +
+                           (0xFFFFFFF0).to_bytes(4, "little") * 2)
+    assert not L.imba_bvh_cache_open(huge.encode()) and "larger than the file" in abi.last_error()
