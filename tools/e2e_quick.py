@@ -19,3 +19,5 @@ for threads in (1, 4):
     for _ in range(5): run()
     dt = time.perf_counter() - t0
     print(os.environ.get('IMBA_LIB_VARIANT', 'base'), "threads", threads, "Mrays/s", round(4 * n * 5 / dt / 1e6, 1), "GB/s", round(4 * n * 5 * 48 / dt / 1e9, 1), flush=True)
+# the ceiling beside it: pinned copies up and down at once, no kernels (bench.raw_pcie_bandwidth)
+print("raw memcpy up+down GB/s", round(bench.raw_pcie_bandwidth(torch.cuda.synchronize), 1))
