@@ -15,6 +15,12 @@
 #include "traverse_core.cuh"
 #include "vcm.cuh"
 
+#ifndef IMBA_VCM_CAM_MIN_BLOCKS
+#define IMBA_VCM_CAM_MIN_BLOCKS 1   /* tuning switch: resident blocks per SM the register allocation of the camera shading kernel aims at */
+#endif
+#ifndef IMBA_VCM_LIGHT_MIN_BLOCKS
+#define IMBA_VCM_LIGHT_MIN_BLOCKS 1
+#endif
 namespace {
 
 __device__ __forceinline__ void add_contribution(float* fb, int pixel, V3 c) {
@@ -164,7 +170,7 @@ __device__ __forceinline__ bool light_vertex(const DeviceShading& S, const VcmPa
 }
 
 template <int ALGO>
-__global__ void __launch_bounds__(128) vcm_light_shade_kernel(const DeviceShading S, const VcmParams* Pd, const DevCamera cam, float4* rays, const int4* hits, VCMState* states,
+__global__ void __launch_bounds__(128, IMBA_VCM_LIGHT_MIN_BLOCKS) vcm_light_shade_kernel(const DeviceShading S, const VcmParams* Pd, const DevCamera cam, float4* rays, const int4* hits, VCMState* states,
                                                               const int* sorted, const int* hit_count_ptr, const int* queue_count_ptr, float4* shadow_rays,
                                                               ShadowState* shadow_states, DevLightVertex* cache, int cache_capacity, int* cache_last,
                                                               unsigned long long* ray_stats, float4* out_rays, VCMState* out_states, int* out_count) {
@@ -528,7 +534,7 @@ __global__ void __launch_bounds__(256) vcm_merge_query_kernel(const DeviceShadin
 }
 
 template <int ALGO>
-__global__ void __launch_bounds__(128) vcm_camera_shade_kernel(const DeviceShading S, const VcmParams* Pd, float4* rays, const int4* hits, VCMState* states, const int* sorted,
+__global__ void __launch_bounds__(128, IMBA_VCM_CAM_MIN_BLOCKS) vcm_camera_shade_kernel(const DeviceShading S, const VcmParams* Pd, float4* rays, const int4* hits, VCMState* states, const int* sorted,
                                                                const int* hit_count_ptr, const int* queue_count_ptr, float4* shadow_rays, ShadowState* shadow_states,
                                                                const DevLightVertex* cache, const GridParams* gp, const int* cells, unsigned table,
                                                                const DevPhoton* photons, const int* merge_found, int merge_stride, float* fb, unsigned long long* ray_stats,
