@@ -209,6 +209,25 @@ def reference_cfg0(cores):
             "threads": cores, "mean_radiance": float(img.mean()) / CFG0["spp"], "kind": "reference host pipeline + restated traversal"}
 
 
+def reference_on_library_cfg0(cores):
+    """configs[0] once more, this time THE UNMODIFIED REFERENCE LINKED AGAINST libimba_b200.so (oracle/_ref/libimba_ref_b200.so, oracle/Makefile:
+    ref_b200): its own loader, SBVH builder, TileScheduler, RayQueue and PathTracer, with the four traversal symbols resolved from the product
+    and the scene in device memory (`--gpu`): every 65 536-ray queue is copied up, traversed and copied down by the reference's own code
+    (ray_queue.h:269-343).  What a maintainer gets from the zero-source-change drop-in; the shading stays on the host's cores."""
+    from tests import refapi
+    if not refapi.have_ref_b200():
+        return {"unavailable": "oracle/_ref/libimba_ref_b200.so not built"}
+    rs = refapi.RefScene(refapi.scene_path("stilllife_proxy"), True, lib=refapi.ref_b200())
+    rs.render(0, CFG0["width"], CFG0["height"], spp=1, iterations=1, threads=cores, tile=CFG0["tile"], max_path_len=CFG0["max_path_len"])
+    img, st = rs.render(0, CFG0["width"], CFG0["height"], spp=1, iterations=CFG0["spp"], threads=cores, tile=CFG0["tile"], max_path_len=CFG0["max_path_len"])
+    rs.close()
+    n = CFG0["width"] * CFG0["height"] * CFG0["spp"]
+    return {"workload": "PT 512x512, 16 spp, max path length 22, tile 256 (65 536-ray queues), stilllife-proxy at detail 0.02, the reference's --gpu path",
+            "samples_per_s": n / st["seconds"], "seconds": st["seconds"], "mrays_s": (st["primary_rays"] + st["shadow_rays"]) / st["seconds"] / 1e6,
+            "threads": cores, "mean_radiance": float(img.mean()) / CFG0["spp"],
+            "kind": "unmodified reference host pipeline, traversal entry points bound to libimba_b200.so (queues cross PCIe per call, shading on the host)"}
+
+
 def ours_cfg0():
     """The same configuration on the device integrator, on the same scene (the fixture the reference's loader exported)."""
     import torch
@@ -668,6 +687,7 @@ def run_ours(args):
                 "gpu_launches": int(launches),
                 "clocks": sampler.summary(),
                 "parity_sample": parity_sample(flat, scene, batches),
+                "cfg0_reference_on_library": reference_on_library_cfg0(cores) if world == 1 else {"unavailable": "timed at N = 1 only"},
                 "pt": pt, "pt_no_overlap": pt_serial, "pt_single_pass": pt_single, "pt_spp4": pt_spp4, "cfg0": ours_cfg0(), "integrators": run_integrators(scene, flat), "scenes": run_extra_scenes(rank), "device_build": device_build,
                 "per_kernel": {name: {"ms": per_kernel_ms[i], "mrays_s": n / per_kernel_ms[i] / 1e3} for i, (name, _) in enumerate(BATCH_ORDER)},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,

@@ -31,6 +31,9 @@ constexpr unsigned FULL = 0xffffffffu;
 #define IMBA_REFILL_LANES 20
 #endif
 constexpr int      REFILL_LANES = IMBA_REFILL_LANES; // refill when fewer lanes than this are active
+#ifndef IMBA_PREFETCH_NEXT
+#define IMBA_PREFETCH_NEXT 0  /* 1 / 2: prefetch the next inner child's node into L1 / L2 before the triangle tests (tuning switch) */
+#endif
 #ifndef IMBA_SMEM_STACK
 #define IMBA_SMEM_STACK 0  /* traversal-stack entries per thread kept in shared memory (tuning switch) */
 #endif
@@ -122,6 +125,20 @@ __global__ void __launch_bounds__(BLOCK_THREADS) trace_kernel(const TraceArgs P)
                 const uint32_t hitmask = node_step(n0, n1, n2, n3, n4, r, tmin, hr.tbest);
                 ngroup = make_uint2(n1.x, (hitmask & 0xff000000u) | (e_imask >> 24));
                 tgroup = make_uint2(n1.y, hitmask & 0x00ffffffu);
+#if IMBA_PREFETCH_NEXT
+                // triangles are tested first and an inner child is visited next: start fetching that node now (tuning switch)
+                if (tgroup.y != 0 && ngroup.y > 0x00ffffffu) {
+                    const uint32_t nbit = 31u - (uint32_t)__clz(ngroup.y);
+                    const uint32_t nslot = (nbit - 24u) ^ (r.octinv4 & 0xffu);
+                    const uint32_t nrel = __popc(ngroup.y & 0xffu & ~(0xffffffffu << nslot));
+                    const char* pf = reinterpret_cast<const char*>(nodes + (size_t)(ngroup.x + nrel) * 5);
+#if IMBA_PREFETCH_NEXT == 2
+                    asm volatile("prefetch.global.L2 [%0];" :: "l"(pf)); asm volatile("prefetch.global.L2 [%0];" :: "l"(pf + 64));
+#else
+                    asm volatile("prefetch.global.L1 [%0];" :: "l"(pf)); asm volatile("prefetch.global.L1 [%0];" :: "l"(pf + 64));
+#endif
+                }
+#endif
             } else {
                 tgroup = ngroup; ngroup = make_uint2(0, 0);
             }
