@@ -13,6 +13,7 @@
  * Ray counts live in device memory (count_ptr), so a whole wavefront loop is enqueued without host synchronisation.
  */
 #include "queue.cuh"
+#include "api_common.h"
 
 namespace {
 
@@ -240,7 +241,6 @@ cudaError_t imba_gather_queue(const int* idx, const int* n_ptr, int n_imm, int c
 /* ---- the same primitives on HOST arrays: RayQueue::{compact_hits, compact_rays, sort_by_material} keep their queues in host
  * memory (ray_queue.h:161-244); these entry points stage the arrays through device memory, run the kernels above and copy the
  * result back in place.  Used by the C++ mirror of RayQueue (include/imba_b200.hpp); the device integrators never come here. */
-#include "api_common.h"
 
 namespace {
 struct DeviceBuf {
