@@ -1,6 +1,6 @@
 """Parity ON THE CONFIGURATION bench.py MEASURES (BASELINE.json configs[1], configs[4]) and on the scenes whose structure is
 larger than L2: every ray of the four 4 Mi-ray bench batches on the full-detail stilllife-proxy (1.52 M triangles) against the
-CPU oracle, 64 Ki random rays on the 2 744-instance scene and on the 4.7 M-triangle terrain, and one VCM light + camera stage
+CPU oracle, 1 Mi random rays on the 2 744-instance scene and on the 4.7 M-triangle terrain, and one VCM light + camera stage
 comparison with the reference's own VCMIntegrator on a 2 744-instance scene loaded by the reference's loader.
 
 Bar (ray_queue.h:254-265, integrator.h:57): closest hit bit-exact (tri_id, inst_id, t, u), occlusion flag-equal, outside the
@@ -98,7 +98,7 @@ def test_bench_closest_and_occluded_batches_are_consistent(bench_setup):
 @pytest.mark.parametrize("which", ["instanced_2744", "terrain_4.7M"])
 def test_large_scenes_match_oracle(which):
     """configs[4]-sized structures: 2 744 rigid instances of Cornell-water (19.4 M instanced triangles, two-level traversal) and a
-    4.7 M-triangle terrain (264 MB of nodes + triangles, larger than L2), 64 Ki random rays each, closest hit and occlusion."""
+    4.7 M-triangle terrain (264 MB of nodes + triangles, larger than L2), 1 Mi random rays each, closest hit and occlusion."""
     import torch
     import bench
     from imbatracer_b200 import api, procedural
@@ -111,7 +111,7 @@ def test_large_scenes_match_oracle(which):
             assert len(flat.instances) == 2744
         else:
             assert flat.tri_count == 4718594 and scene.stats()["bytes"] > 126e6
-        rays = raygen.random_rays(flat, 1 << 16, 23)
+        rays = raygen.random_rays(flat, 1 << 20, 23)
         got = api.hits_from_device(scene.trace(api.rays_to_device(rays)))
         occ = api.hits_from_device(scene.trace(api.rays_to_device(rays), any_hit=True))
         torch.cuda.synchronize()
