@@ -35,6 +35,8 @@ struct DevLight {            // 7 x float4
 struct DeviceShading {
     const int*    mesh_vertex_base; const int* mesh_tri_base;
     const float4* vertices; const float4* normals; const float2* texcoords; const float4* geom_normals; const int4* indices;
+    const float4* shade_tris;   // 8 x float4 (one 128-byte line) per global triangle: everything calculate_intersection reads of it, gathered
+                                // once at upload -- q0 v0|material id, q1 v1|uv0.x, q2 v2|uv0.y, q3 n0|uv1.x, q4 n1|uv1.y, q5 n2|uv2.x, q6 gn|uv2.y, q7 unused
     const int*    inst_mesh; const float4* inst_mat; const float4* inst_inv; // 3 float4 per instance each
     const float4* materials;  // imba_material as 5 x float4
     const DevLight* lights;
@@ -89,32 +91,32 @@ __device__ __forceinline__ float2 lerp2(float2 a, float2 b, float2 c, float u, f
 
 /* integrator.h:71-123 */
 __device__ __forceinline__ Isect calc_intersection(const DeviceShading& S, float4 ro, float4 rd, int tri_id, int inst_id, float t, float u) {
-    const int mesh = __ldg(S.inst_mesh + inst_id);
-    const int local_tri = tri_id - __ldg(S.mesh_tri_base + mesh);
-    const int vbase = __ldg(S.mesh_vertex_base + mesh);
-    const int4 idx = __ldg(S.indices + __ldg(S.mesh_tri_base + mesh) + local_tri);
-    const int i0 = vbase + idx.x, i1 = vbase + idx.y, i2 = vbase + idx.z;
+    // The reference follows instance -> mesh -> index record -> three vertices / normals / texture coordinates -> geometric normal
+    // (integrator.h:72-107): four dependent levels and about ten cache lines per hit.  The hit carries the GLOBAL triangle id, so the
+    // device reads one 128-byte record per triangle instead (shade_data.cu: same floats, same arithmetic below).
+    const float4* q = S.shade_tris + 8 * (size_t)tri_id;
+    const float4 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2), q3 = __ldg(q + 3), q4 = __ldg(q + 4), q5 = __ldg(q + 5), q6 = __ldg(q + 6);
     const float4 m0 = __ldg(S.inst_inv + 3 * inst_id), m1 = __ldg(S.inst_inv + 3 * inst_id + 1), m2 = __ldg(S.inst_inv + 3 * inst_id + 2);
     const V3 org = v3(ro), out_dir = v3(rd);
     const V3 pos = org + t * out_dir;
     const V3 local_pos = v3(m0.x * pos.x + m0.y * pos.y + m0.z * pos.z + m0.w * 1.0f,
                             m1.x * pos.x + m1.y * pos.y + m1.z * pos.z + m1.w * 1.0f,
                             m2.x * pos.x + m2.y * pos.y + m2.z * pos.z + m2.w * 1.0f);
-    const V3 v0 = v3(__ldg(S.vertices + i0));
-    const V3 e1 = v3(__ldg(S.vertices + i1)) - v0, e2 = v3(__ldg(S.vertices + i2)) - v0;
+    const V3 v0 = v3(q0);
+    const V3 e1 = v3(q1) - v0, e2 = v3(q2) - v0;
     const float v = dot(local_pos - v0 - u * e1, e2) / dot(e2, e2);
     Isect r;
-    r.uv = lerp2(__ldg(S.texcoords + i0), __ldg(S.texcoords + i1), __ldg(S.texcoords + i2), u, v);
-    const V3 n0 = v3(__ldg(S.normals + i0)), n1 = v3(__ldg(S.normals + i1)), n2 = v3(__ldg(S.normals + i2));
+    r.uv = lerp2(make_float2(q1.w, q2.w), make_float2(q3.w, q4.w), make_float2(q5.w, q6.w), u, v);
+    const V3 n0 = v3(q3), n1 = v3(q4), n2 = v3(q5);
     const V3 ln = n0 * (1 - u - v) + n1 * u + n2 * v;
     // row vector * 3x4 matrix (float3x4.h:41-46): transforms normals by the inverse transpose
     const V3 nw = v3(m0.x * ln.x + m1.x * ln.y + m2.x * ln.z, m0.y * ln.x + m1.y * ln.y + m2.y * ln.z, m0.z * ln.x + m1.z * ln.y + m2.z * ln.z);
-    const V3 g = v3(__ldg(S.geom_normals + __ldg(S.mesh_tri_base + mesh) + local_tri));
+    const V3 g = v3(q6);
     const V3 gw = v3(m0.x * g.x + m1.x * g.y + m2.x * g.z, m0.y * g.x + m1.y * g.y + m2.y * g.z, m0.z * g.x + m1.z * g.y + m2.z * g.z);
     r.pos = pos; r.out_dir = -normalize(out_dir);
     r.normal = normalize(nw); r.geom_normal = normalize(gw);
     local_coordinates(r.normal, r.u_tangent, r.v_tangent);
-    r.mat = idx.w;
+    r.mat = __float_as_int(q0.w);
     // Material::bump (materials.h:34-55)
     const float4 mh = __ldg(S.materials + 5 * r.mat);
     const int bump = __float_as_int(mh.z);

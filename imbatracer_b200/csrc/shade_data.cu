@@ -45,6 +45,26 @@ int imba_shading_upload(imba_scene* s, const imba_scene_desc* d) {
     v.texcoords = up<float2>(st, d->texcoords, nv, ok);
     v.geom_normals = up<float4>(st, d->geom_normals, nt, ok);
     v.indices = up<int4>(st, d->indices, nt, ok);
+    {   // one 128-byte record per triangle with everything calc_intersection reads of it (shade.cuh: DeviceShading::shade_tris)
+        std::vector<float> rec(32 * (size_t)nt, 0.0f);
+        for (int mi = 0; mi < d->mesh_count; ++mi) {
+            const int vb = d->mesh_vertex_base[mi];
+            for (int t = d->mesh_tri_base[mi]; t < d->mesh_tri_base[mi + 1]; ++t) {
+                const int32_t* q = d->indices + 4 * (size_t)t;
+                float* o = rec.data() + 32 * (size_t)t;
+                for (int k = 0; k < 3; ++k) {
+                    const size_t vi = (size_t)vb + q[k];
+                    memcpy(o + 4 * k, d->vertices + 4 * vi, 12);            // q0..q2: positions
+                    memcpy(o + 12 + 4 * k, d->normals + 4 * vi, 12);        // q3..q5: shading normals
+                    o[4 * (1 + 2 * k) + 3] = d->texcoords[2 * vi];          // q1.w q3.w q5.w: u of corner k
+                    o[4 * (2 + 2 * k) + 3] = d->texcoords[2 * vi + 1];      // q2.w q4.w q6.w: v of corner k
+                }
+                memcpy(o + 3, q + 3, 4);                                    // q0.w: material id
+                memcpy(o + 24, d->geom_normals + 4 * (size_t)t, 12);        // q6: geometric normal
+            }
+        }
+        v.shade_tris = up<float4>(st, rec.data(), 8 * (size_t)nt, ok);
+    }
     std::vector<int> im(d->instance_count); std::vector<float> mat(12 * (size_t)d->instance_count), inv(12 * (size_t)d->instance_count);
     for (int i = 0; i < d->instance_count; ++i) {
         im[i] = d->instances[i].mesh_id;
