@@ -95,7 +95,7 @@ LIGHT_VERTEX = np.dtype([("pos", "<f4", 3), ("path_length", "<i4"), ("out_dir", 
 assert VCM_STATE.itemsize == 48 and LIGHT_VERTEX.itemsize == 112
 SHADOW_STATE = np.dtype([("pixel_id", "<i4"), ("throughput", "<f4", 3)])
 assert PT_STATE.itemsize == 40 and SHADOW_STATE.itemsize == 16
-TRI48 = np.dtype([("v0", "<f4", 3), ("id", "<i4"), ("e1", "<f4", 3), ("pad0", "<f4"), ("e2", "<f4", 3), ("pad1", "<f4")])
+TRI48 = np.dtype([("v0", "<f4", 3), ("id", "<i4"), ("e1", "<f4", 3), ("nx", "<f4"), ("e2", "<f4", 3), ("ny", "<f4")])
 INST64 = np.dtype([("m", "<f4", 12), ("inst_id", "<i4"), ("root", "<i4"), ("pad", "<i4", 2)])
 assert RAY.itemsize == 32 and HIT.itemsize == 16 and NODE4.itemsize == 112 and NODE2.itemsize == 56
 assert INSTANCE_NODE.itemsize == 64 and MATERIAL.itemsize == C.sizeof(Material) == 80 and LIGHT.itemsize == C.sizeof(Light) == 80

@@ -94,7 +94,7 @@ struct Parser {
                     if (id < 0) continue;
                     Tri48 tr; memset(&tr, 0, sizeof(tr));
                     for (int a = 0; a < 3; ++a) { tr.v0[a] = f[4 * a + l]; tr.e1[a] = f[12 + 4 * a + l]; tr.e2[a] = f[24 + 4 * a + l]; }
-                    tr.id = id;
+                    tr.id = id; IMBA_TRI48_FINISH(tr);
                     Box pb = tri_bounds(tr); pb.clip(box);
                     t.prims.push_back((int)tri_store->size()); tri_store->push_back(tr); t.prim_box.push_back(pb); ++count;
                 }
@@ -109,7 +109,7 @@ struct Parser {
                 Tri48 tr; memset(&tr, 0, sizeof(tr));
                 const float v0[3] = { p[0].x, p[0].y, p[0].z }, v1[3] = { p[1].x, p[1].y, p[1].z }, v2[3] = { p[2].x, p[2].y, p[2].z };
                 for (int a = 0; a < 3; ++a) { tr.v0[a] = v0[a]; tr.e1[a] = v0[a] - v1[a]; tr.e2[a] = v2[a] - v0[a]; }
-                tr.id = f2i(p[1].w);
+                tr.id = f2i(p[1].w); IMBA_TRI48_FINISH(tr);
                 Box pb; pb.reset(); pb.grow(v0); pb.grow(v1); pb.grow(v2); pb.clip(box);
                 t.prims.push_back((int)tri_store->size()); tri_store->push_back(tr); t.prim_box.push_back(pb); ++count;
                 if ((uint32_t)f2i(p[2].w) == 0x80000000u) break;

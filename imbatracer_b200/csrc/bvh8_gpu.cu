@@ -226,8 +226,9 @@ __global__ void emit_level_kernel(EmitArgs A, uint32_t lo, uint32_t hi) {
                 float4 a, b, c3; tri_verts(A.m, t, a, b, c3);
                 Tri48 o;
                 o.v0[0] = a.x; o.v0[1] = a.y; o.v0[2] = a.z; o.id = A.m.tbase + t;
-                o.e1[0] = a.x - b.x; o.e1[1] = a.y - b.y; o.e1[2] = a.z - b.z; o.pad0 = 0.0f;
-                o.e2[0] = c3.x - a.x; o.e2[1] = c3.y - a.y; o.e2[2] = c3.z - a.z; o.pad1 = 0.0f;
+                o.e1[0] = a.x - b.x; o.e1[1] = a.y - b.y; o.e1[2] = a.z - b.z;
+                o.e2[0] = c3.x - a.x; o.e2[1] = c3.y - a.y; o.e2[2] = c3.z - a.z;
+                IMBA_TRI48_FINISH(o);
                 A.tris[prim_base + prim_off + i] = o;
             }
             prim_off += cnt;

@@ -7,7 +7,7 @@
  *   type 1 = BVH  (traversal_gpu::Node, 56 B; prims = Vec4, 3 per triangle)      type 2 = MBVH (traversal_cpu::Node, 112 B;
  *            prims = Vec4, 13 per packet + sentinels); indices inside a block are file-local (node 0 = mesh root, triangle ids
  *            start at 0), load_bvh.cpp:199-224
- *   type 3 = (new) the compressed 8-wide layout of this library: Node8 (80 B) + Tri48 (48 B), csrc/bvh8.h, so that a cache
+ *   type 3 = (new) the compressed 8-wide layout of this library: Node8 (80 B) + Tri48 (48 B, incl. nx / ny), csrc/bvh8.h, so that a cache
  *            written once skips the conversion; unknown block types are skipped by the reference's reader (locate_block).
  */
 #include <cstdio>

@@ -40,7 +40,9 @@ constexpr int      REFILL_LANES = IMBA_REFILL_LANES; // refill when fewer lanes 
 
 /* MODE 0 = closest hit, 1 = any hit, 2 = any hit fused with process_shadow_rays (integrator.h:49-63): no hit record is
  * written; an unoccluded ray adds its ShadowState throughput to the accumulation buffer; slots whose pixel_id < 0 are skipped. */
-template <int MODE, bool MASKS, bool STATS>
+/* FLAT = the scene is one identity instance and traversal starts at its mesh root (P.flat_inst >= 0): the instance level --
+ * entering, the sentinel, the saved world-space ray -- is compiled out of that kernel. */
+template <int MODE, bool MASKS, bool STATS, bool FLAT>
 // (an explicit minimum of 1 block per SM makes ptxas spend 92-96 registers; leaving it open gives 56 and 9 resident blocks)
 #ifdef IMBA_MIN_BLOCKS
 __global__ void __launch_bounds__(BLOCK_THREADS, IMBA_MIN_BLOCKS) trace_kernel(const TraceArgs P) {
@@ -94,7 +96,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS) trace_kernel(const TraceArgs P)
                     ray_idx = (int)i;
                     const float4 o = __ldcs(P.rays + 2 * i), d = __ldcs(P.rays + 2 * i + 1);
                     r.ox = o.x; r.oy = o.y; r.oz = o.z; r.dx = d.x; r.dy = d.y; r.dz = d.z;
-                    if (P.flat_inst >= 0) { // the identity transform of the skipped instance turns -0 into +0 (1 * x + 0)
+                    if (FLAT || P.flat_inst >= 0) { // the identity transform of the skipped instance turns -0 into +0 (1 * x + 0)
                         r.ox += 0.0f; r.oy += 0.0f; r.oz += 0.0f; r.dx += 0.0f; r.dy += 0.0f; r.dz += 0.0f;
                     }
                     r.finish();
@@ -148,17 +150,19 @@ __global__ void __launch_bounds__(BLOCK_THREADS) trace_kernel(const TraceArgs P)
             while (tgroup.y != 0) {
                 const uint32_t bit = 31u - (uint32_t)__clz(tgroup.y);
                 tgroup.y &= ~(1u << bit);
-                if (cur_inst < 0) {
+                if (!FLAT && cur_inst < 0) {
                     // top level: enter the instance (ray * inverse transform, cpu_adapter.cpp:356-365)
                     if (ngroup.y > 0x00ffffffu) STACK_PUSH(ngroup);
                     if (tgroup.y != 0) STACK_PUSH(tgroup);
                     // the world-space ray (with its reciprocals and octant) goes onto the stack under the sentinel: leaving the instance
                     // pops it back instead of reloading the ray from the queue and dividing three times again
+#ifndef IMBA_RELOAD_WORLD_RAY
                     STACK_PUSH(make_uint2(__float_as_uint(r.ox), __float_as_uint(r.oy)));
                     STACK_PUSH(make_uint2(__float_as_uint(r.oz), __float_as_uint(r.dx)));
                     STACK_PUSH(make_uint2(__float_as_uint(r.dy), __float_as_uint(r.dz)));
                     STACK_PUSH(make_uint2(__float_as_uint(r.ix), __float_as_uint(r.iy)));
                     STACK_PUSH(make_uint2(__float_as_uint(r.iz), r.octinv4));
+#endif
                     STACK_PUSH(make_uint2(0xffffffffu, 0u));
                     if (STATS) { st_sp = max(st_sp, (uint32_t)sp); ++st_insts; }
                     const float4* ip = P.insts + (size_t)(tgroup.x + bit) * 4;
@@ -182,11 +186,16 @@ __global__ void __launch_bounds__(BLOCK_THREADS) trace_kernel(const TraceArgs P)
                 for (;;) {
                     if (sp == 0) { done = true; break; }
                     const uint2 e = STACK_POP();
-                    if (e.y == 0u) { // sentinel: leave the instance, restore the world-space ray saved under it
+                    if (!FLAT && e.y == 0u) { // sentinel: leave the instance, restore the world-space ray saved under it
+#ifndef IMBA_RELOAD_WORLD_RAY
                         const uint2 s4 = STACK_POP(), s3 = STACK_POP(), s2 = STACK_POP(), s1 = STACK_POP(), s0 = STACK_POP();
                         r.ox = __uint_as_float(s0.x); r.oy = __uint_as_float(s0.y); r.oz = __uint_as_float(s1.x); r.dx = __uint_as_float(s1.y);
                         r.dy = __uint_as_float(s2.x); r.dz = __uint_as_float(s2.y); r.ix = __uint_as_float(s3.x); r.iy = __uint_as_float(s3.y);
                         r.iz = __uint_as_float(s4.x); r.octinv4 = s4.y;
+#else   // round-1 behaviour (A/B switch): reload the ray from the queue and divide again
+                        const float4 o = __ldg(P.rays + 2 * ray_idx), d = __ldg(P.rays + 2 * ray_idx + 1);
+                        r.ox = o.x; r.oy = o.y; r.oz = o.z; r.dx = d.x; r.dy = d.y; r.dz = d.z; r.finish();
+#endif
                         cur_inst = -1;
                         continue;
                     }
@@ -226,10 +235,15 @@ __global__ void __launch_bounds__(BLOCK_THREADS) trace_kernel(const TraceArgs P)
 #include "traverse_coop.cuh"
 #endif
 
+#ifndef IMBA_NO_FLAT_KERNEL
+#define IMBA_NO_FLAT_KERNEL 0   // A/B switch: 1 = flat scenes run the two-level kernel (round-2a behaviour)
+#endif
+
 template <int ANY, bool MASKS, bool STATS>
 cudaError_t launch(const TraceArgs& a, int grid, cudaStream_t s) {
 #ifndef IMBA_COOP_TRACE
-    trace_kernel<ANY, MASKS, STATS><<<grid, BLOCK_THREADS, 0, s>>>(a);
+    if (a.flat_inst >= 0 && !IMBA_NO_FLAT_KERNEL) trace_kernel<ANY, MASKS, STATS, true><<<grid, BLOCK_THREADS, 0, s>>>(a);
+    else                  trace_kernel<ANY, MASKS, STATS, false><<<grid, BLOCK_THREADS, 0, s>>>(a);
 #else
     const int smem = (BLOCK_THREADS / 32) * (a.flat_inst >= 0 ? COOP_WARP_BYTES_FLAT : COOP_WARP_BYTES_INST);
     trace_coop_kernel<ANY, MASKS, STATS><<<grid, BLOCK_THREADS, smem, s>>>(a);
@@ -241,7 +255,8 @@ template <int ANY, bool MASKS, bool STATS>
 int occupancy(bool flat) {
     int n = 0;
 #ifndef IMBA_COOP_TRACE
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, trace_kernel<ANY, MASKS, STATS>, BLOCK_THREADS, 0);
+    if (flat && !IMBA_NO_FLAT_KERNEL) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, trace_kernel<ANY, MASKS, STATS, true>, BLOCK_THREADS, 0);
+    else      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, trace_kernel<ANY, MASKS, STATS, false>, BLOCK_THREADS, 0);
 #else
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, trace_coop_kernel<ANY, MASKS, STATS>, BLOCK_THREADS,
                                                   (BLOCK_THREADS / 32) * (flat ? COOP_WARP_BYTES_FLAT : COOP_WARP_BYTES_INST));

@@ -130,8 +130,12 @@ template <bool MASKS>
 __device__ __forceinline__ bool tri_test(const TraceArgs& P, const float4 a, const float4 b, const float4 c, const RayRegs& r, float tmin, int cur_inst, HitRegs& h) {
     float& tbest = h.tbest; float& ubest = h.ubest; int& tri_best = h.tri_best; int& inst_best = h.inst_best;
     const int tri_id = __float_as_int(a.w);
-    // n = e1 x e2, unfused (what cpu_adapter.cpp:149 stores)
+    // n = e1 x e2, unfused (what cpu_adapter.cpp:149 stores): x and y travel in the record's padding (bvh8.h), z is computed
+#ifndef IMBA_TRI_RECOMPUTE_N
+    const float nx = b.w, ny = c.w, nz = b.x * c.y - b.y * c.x;
+#else
     const float nx = b.y * c.z - b.z * c.y, ny = b.z * c.x - b.x * c.z, nz = b.x * c.y - b.y * c.x;
+#endif
     const float cx = a.x - r.ox, cy = a.y - r.oy, cz = a.z - r.oz;
     const float rx = __fmaf_rn(r.dy, cz, -(r.dz * cy));
     const float ry = __fmaf_rn(r.dz, cx, -(r.dx * cz));

@@ -34,6 +34,10 @@ def test_converted_structure_invariants(name, layout):
     # every triangle id of the scene is present at least once; ids stay global
     ids = b8.tris["id"][:-1]
     assert set(ids.tolist()) == set(range(flat.tri_count))
+    # the record carries the first two components of n = e1 x e2, computed unfused in float32 (bvh8.h; tri_test reads them)
+    t = b8.tris[:-1]; e1, e2 = t["e1"], t["e2"]
+    assert np.array_equal(t["nx"].view(np.uint32), (e1[:, 1] * e2[:, 2] - e1[:, 2] * e2[:, 1]).view(np.uint32))
+    assert np.array_equal(t["ny"].view(np.uint32), (e1[:, 2] * e2[:, 0] - e1[:, 0] * e2[:, 2]).view(np.uint32))
     # meta encoding: inner children have 0b001_11sss with sss = slot and imask bit set; leaves unary counts 1/3/7
     for s in range(8):
         m = n["meta"][:, s].astype(np.int32)
