@@ -33,6 +33,9 @@ struct Box3 {
 inline float i2f(int32_t i) { float f; memcpy(&f, &i, 4); return f; }
 inline void set_bb(imba_bbox& d, const Box3& b) { d.lo_x = b.lo[0]; d.lo_y = b.lo[1]; d.lo_z = b.lo[2]; d.hi_x = b.hi[0]; d.hi_y = b.hi[1]; d.hi_z = b.hi[2]; }
 
+// triangles per leaf of the binary tree (tuning knob IMBA_MAX_LEAF, 1..3; the 8-wide collapse may merge leaves again)
+static const int MAX_LEAF = getenv("IMBA_MAX_LEAF") ? std::min(3, std::max(1, atoi(getenv("IMBA_MAX_LEAF")))) : 1;
+
 struct Builder {
     const Box3* boxes; std::vector<int> prims; int max_leaf;
     std::vector<imba_node2>& nodes; int node_offset; // indices written = local index + node_offset
@@ -162,7 +165,7 @@ extern "C" imba_accel* imba_accel_build(const imba_scene_desc* d) {
                 return off;
             }
         } leaf; leaf.d = d; leaf.vbase = vbase; leaf.tbase = tbase; leaf.tris = &out->tris;
-        Builder b(boxes.data(), nt, 3, out->nodes, 0, &leaf);
+        Builder b(boxes.data(), nt, MAX_LEAF, out->nodes, 0, &leaf);
         mesh_root[m] = b.run();
         mesh_box[m].reset(); for (int t = 0; t < nt; ++t) mesh_box[m].grow(boxes[t]);
     }

@@ -203,7 +203,7 @@ void split_leaf(Tree& t, int tn) {
 
 constexpr float COST_NODE = 1.0f;
 // cost of one primitive test relative to one node visit; tuning knob IMBA_COST_PRIM
-static const float COST_PRIM = getenv("IMBA_COST_PRIM") ? (float)atof(getenv("IMBA_COST_PRIM")) : 0.5f;
+static const float COST_PRIM = getenv("IMBA_COST_PRIM") ? (float)atof(getenv("IMBA_COST_PRIM")) : 0.8f;
 
 /* SAH-optimal collapse.  Works on a binarised copy of the tree's topology: bin[n] = {left, right} for inner nodes. */
 struct Collapse {

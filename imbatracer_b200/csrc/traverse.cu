@@ -38,17 +38,21 @@ constexpr int      REFILL_LANES = IMBA_REFILL_LANES; // refill when fewer lanes 
 #define IMBA_SMEM_STACK 0  /* traversal-stack entries per thread kept in shared memory (tuning switch) */
 #endif
 
+/* Index of the highest set bit (x != 0): one FLO; `31 - __clz(x)` costs a second instruction that the compiler does not fold. */
+__device__ __forceinline__ uint32_t top_bit(uint32_t x) {
+#ifndef IMBA_NO_BFIND
+    uint32_t b; asm("bfind.u32 %0, %1;" : "=r"(b) : "r"(x)); return b;
+#else
+    return 31u - (uint32_t)__clz(x);
+#endif
+}
+
 /* MODE 0 = closest hit, 1 = any hit, 2 = any hit fused with process_shadow_rays (integrator.h:49-63): no hit record is
  * written; an unoccluded ray adds its ShadowState throughput to the accumulation buffer; slots whose pixel_id < 0 are skipped. */
 /* FLAT = the scene is one identity instance and traversal starts at its mesh root (P.flat_inst >= 0): the instance level --
- * entering, the sentinel, the saved world-space ray -- is compiled out of that kernel. */
+ * entering, the sentinel, the saved world-space ray, the instance id of the best hit -- is compiled out. */
 template <int MODE, bool MASKS, bool STATS, bool FLAT>
-// (an explicit minimum of 1 block per SM makes ptxas spend 92-96 registers; leaving it open gives 56 and 9 resident blocks)
-#ifdef IMBA_MIN_BLOCKS
-__global__ void __launch_bounds__(BLOCK_THREADS, IMBA_MIN_BLOCKS) trace_kernel(const TraceArgs P) {
-#else
-__global__ void __launch_bounds__(BLOCK_THREADS) trace_kernel(const TraceArgs P) {
-#endif
+__device__ __forceinline__ void trace_body(const TraceArgs& P) {
     constexpr bool ANY = MODE != 0;
     constexpr bool RESOLVE = MODE == 2;
     const int ray_count = P.count_ptr ? *P.count_ptr * P.count_mul : P.count;
@@ -114,7 +118,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS) trace_kernel(const TraceArgs P)
             if (ngroup.y > 0x00ffffffu) {
                 // pick the nearest pending inner child of the current node group
                 const uint32_t hits = ngroup.y;
-                const uint32_t bit = 31u - (uint32_t)__clz(hits);
+                const uint32_t bit = top_bit(hits);
                 ngroup.y &= ~(1u << bit);
                 if (ngroup.y > 0x00ffffffu) { STACK_PUSH(ngroup); if (STATS) st_sp = max(st_sp, (uint32_t)sp); }
                 const uint32_t slot = (bit - 24u) ^ (r.octinv4 & 0xffu);
@@ -148,7 +152,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS) trace_kernel(const TraceArgs P)
             // ---- primitives of the current group -----------------------------------------------
             bool done = false;
             while (tgroup.y != 0) {
-                const uint32_t bit = 31u - (uint32_t)__clz(tgroup.y);
+                const uint32_t bit = top_bit(tgroup.y);
                 tgroup.y &= ~(1u << bit);
                 if (!FLAT && cur_inst < 0) {
                     // top level: enter the instance (ray * inverse transform, cpu_adapter.cpp:356-365)
@@ -177,7 +181,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS) trace_kernel(const TraceArgs P)
                 const float4* tp = tris + (size_t)(tgroup.x + bit) * 3;
                 const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
                 if (STATS) ++st_tris;
-                if (!tri_test<MASKS>(P, a, b, c, r, tmin, cur_inst, hr)) continue;
+                if (!tri_test<MASKS, FLAT>(P, a, b, c, r, tmin, cur_inst, hr)) continue;
                 if (ANY) { done = true; break; }
             }
 
@@ -212,7 +216,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS) trace_kernel(const TraceArgs P)
                     }
                 } else {
                     int4 h;
-                    if (hr.tri_best != IMBA_NO_HIT) h = make_int4(hr.tri_best, hr.inst_best, __float_as_int(hr.tbest), __float_as_int(hr.ubest));
+                    if (hr.tri_best != IMBA_NO_HIT) h = make_int4(hr.tri_best, FLAT ? P.flat_inst : hr.inst_best, __float_as_int(hr.tbest), __float_as_int(hr.ubest));
                     else                           h = make_int4(-1, -1, __float_as_int(hr.tbest), 0);
                     __stcs(P.hits + ray_idx, h);
                 }
@@ -227,9 +231,26 @@ __global__ void __launch_bounds__(BLOCK_THREADS) trace_kernel(const TraceArgs P)
     }
 }
 
-
 #undef STACK_PUSH
 #undef STACK_POP
+
+/* Register budgets.  Two-level kernel: no explicit minimum (an explicit 1 makes ptxas spend 92-96 registers; open it takes 56 =
+ * 9 resident blocks; 48 spills).  Flat kernel: without the instance level it fits 48 registers without spilling, 10 resident
+ * blocks = 40 warps per SM: +3.4 % on the bench batches (11 / 12 blocks spill: -3 %). */
+#ifndef IMBA_FLAT_MIN_BLOCKS
+#define IMBA_FLAT_MIN_BLOCKS 10
+#endif
+#ifndef IMBA_FLAT_RESOLVE_TIGHT
+#define IMBA_FLAT_RESOLVE_TIGHT 0   // the fused resolve mode and the counting variants spill at 48 registers: they keep 56
+#endif
+template <int MODE, bool MASKS, bool STATS>
+#ifdef IMBA_MIN_BLOCKS
+__global__ void __launch_bounds__(BLOCK_THREADS, IMBA_MIN_BLOCKS) trace_kernel(const TraceArgs P) { trace_body<MODE, MASKS, STATS, false>(P); }
+#else
+__global__ void __launch_bounds__(BLOCK_THREADS) trace_kernel(const TraceArgs P) { trace_body<MODE, MASKS, STATS, false>(P); }
+#endif
+template <int MODE, bool MASKS, bool STATS>
+__global__ void __launch_bounds__(BLOCK_THREADS, (STATS || (MODE == 2 && !IMBA_FLAT_RESOLVE_TIGHT)) ? 9 : IMBA_FLAT_MIN_BLOCKS) trace_flat_kernel(const TraceArgs P) { trace_body<MODE, MASKS, STATS, true>(P); }
 
 #ifdef IMBA_COOP_TRACE
 #include "traverse_coop.cuh"
@@ -242,8 +263,8 @@ __global__ void __launch_bounds__(BLOCK_THREADS) trace_kernel(const TraceArgs P)
 template <int ANY, bool MASKS, bool STATS>
 cudaError_t launch(const TraceArgs& a, int grid, cudaStream_t s) {
 #ifndef IMBA_COOP_TRACE
-    if (a.flat_inst >= 0 && !IMBA_NO_FLAT_KERNEL) trace_kernel<ANY, MASKS, STATS, true><<<grid, BLOCK_THREADS, 0, s>>>(a);
-    else                  trace_kernel<ANY, MASKS, STATS, false><<<grid, BLOCK_THREADS, 0, s>>>(a);
+    if (a.flat_inst >= 0 && !IMBA_NO_FLAT_KERNEL) trace_flat_kernel<ANY, MASKS, STATS><<<grid, BLOCK_THREADS, 0, s>>>(a);
+    else                  trace_kernel<ANY, MASKS, STATS><<<grid, BLOCK_THREADS, 0, s>>>(a);
 #else
     const int smem = (BLOCK_THREADS / 32) * (a.flat_inst >= 0 ? COOP_WARP_BYTES_FLAT : COOP_WARP_BYTES_INST);
     trace_coop_kernel<ANY, MASKS, STATS><<<grid, BLOCK_THREADS, smem, s>>>(a);
@@ -255,8 +276,8 @@ template <int ANY, bool MASKS, bool STATS>
 int occupancy(bool flat) {
     int n = 0;
 #ifndef IMBA_COOP_TRACE
-    if (flat && !IMBA_NO_FLAT_KERNEL) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, trace_kernel<ANY, MASKS, STATS, true>, BLOCK_THREADS, 0);
-    else      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, trace_kernel<ANY, MASKS, STATS, false>, BLOCK_THREADS, 0);
+    if (flat && !IMBA_NO_FLAT_KERNEL) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, trace_flat_kernel<ANY, MASKS, STATS>, BLOCK_THREADS, 0);
+    else      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, trace_kernel<ANY, MASKS, STATS>, BLOCK_THREADS, 0);
 #else
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, trace_coop_kernel<ANY, MASKS, STATS>, BLOCK_THREADS,
                                                   (BLOCK_THREADS / 32) * (flat ? COOP_WARP_BYTES_FLAT : COOP_WARP_BYTES_INST));

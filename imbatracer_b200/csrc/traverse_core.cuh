@@ -126,7 +126,9 @@ __device__ __forceinline__ void enter_instance(RayRegs& r, const float4 m0, cons
 }
 
 /* Tests one triangle (a = v0|id, b = e1, c = e2) and updates the hit if (t, tri, inst) is lexicographically smaller. */
-template <bool MASKS>
+/* ONE_INST: every triangle belongs to the same instance (flat scenes), so the instance id neither takes part in the tie rule
+ * nor needs a register; the caller fills it in when it writes the hit. */
+template <bool MASKS, bool ONE_INST = false>
 __device__ __forceinline__ bool tri_test(const TraceArgs& P, const float4 a, const float4 b, const float4 c, const RayRegs& r, float tmin, int cur_inst, HitRegs& h) {
     float& tbest = h.tbest; float& ubest = h.ubest; int& tri_best = h.tri_best; int& inst_best = h.inst_best;
     const int tri_id = __float_as_int(a.w);
@@ -145,14 +147,16 @@ __device__ __forceinline__ bool tri_test(const TraceArgs& P, const float4 a, con
     const uint32_t sgn = __float_as_uint(det) & 0x80000000u;
     const float U = xorf(dot_f(rx, ry, rz, c.x, c.y, c.z), sgn);
     const float V = xorf(dot_f(rx, ry, rz, b.x, b.y, b.z), sgn);
-    if (!(U >= 0.0f) || !(V >= 0.0f) || !(U + V <= adet) || det == 0.0f) return false;
+    // (det == 0 is decided with the second group of tests: a degenerate candidate passes the first group only with U = V = 0)
+    if (!(U >= 0.0f) || !(V >= 0.0f) || !(U + V <= adet)) return false;
     const float T = xorf(dot_f(nx, ny, nz, cx, cy, cz), sgn);
-    if (!(T >= adet * tmin) || !(T <= adet * tbest * IMBA_T_PREFILTER)) return false;
+    if (!(T >= adet * tmin) || !(T <= adet * tbest * IMBA_T_PREFILTER) || det == 0.0f) return false;
     const float inv = 1.0f / adet;
     const float t = T * inv, u = U * inv;
-    if (!(t < tbest || (t == tbest && (tri_id < tri_best || (tri_id == tri_best && cur_inst < inst_best))))) return false;
+    if (ONE_INST) { if (!(t < tbest || (t == tbest && tri_id < tri_best))) return false; }
+    else if (!(t < tbest || (t == tbest && (tri_id < tri_best || (tri_id == tri_best && cur_inst < inst_best))))) return false;
     if (MASKS && !mask_opaque<MASKS>(P, tri_id, u, V * inv)) return false;
-    tbest = t; ubest = u; tri_best = tri_id; inst_best = cur_inst;
+    tbest = t; ubest = u; tri_best = tri_id; if (!ONE_INST) inst_best = cur_inst;
     return true;
 }
 

@@ -17,6 +17,6 @@ tail -3 gpurun_out/ncu_list.log
 fi
 if [ "$1" = "full" ]; then
 python bench.py --steps 2 --warmup 3 > gpurun_out/plain2.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:trace_kernel -s 29 -c 4 -o gpurun_out/prof python bench.py --steps 2 --warmup 3 > gpurun_out/ncu_full.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:trace_.*kernel -s 29 -c 4 -o gpurun_out/prof python bench.py --steps 2 --warmup 3 > gpurun_out/ncu_full.log 2>&1
 tail -3 gpurun_out/ncu_full.log
 fi

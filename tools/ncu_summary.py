@@ -51,7 +51,7 @@ def main():
     if len(sys.argv) > 3 and len(data) == 4:
         ki = hdr.index("Kernel Name") if "Kernel Name" in hdr else None
         names = [r[ki] for r in data]
-        closest = ["trace_kernel<0" in x for x in names]
+        closest = ["trace_kernel<0" in x or "trace_flat_kernel<0" in x for x in names]
         pick = [i for i in range(4) if closest[i] and closest[(i - 1) % 4]]
         if len(pick) == 1:
             i = pick[0]
