@@ -8,9 +8,24 @@
 #include "bvh8.h"
 #include "kernels.h"
 
+/* Reciprocal of a direction component.  It feeds the node tests only (conservative, IMBA_ROBUST_TFAR_DEV), never the triangle test,
+ * so the 1-ulp MUFU.RCP replaces the IEEE division (about 12 instructions each, three per ray and per instance entered). */
+#ifndef IMBA_FAST_RCP
+#define IMBA_FAST_RCP 1
+#endif
 __device__ __forceinline__ float safe_rcp(float d) {
-    return 1.0f / (fabsf(d) > IMBA_RCP_EPS ? d : copysignf(IMBA_RCP_EPS, d));
+    const float c = fabsf(d) > IMBA_RCP_EPS ? d : copysignf(IMBA_RCP_EPS, d);
+#if IMBA_FAST_RCP
+    float r; asm("rcp.approx.f32 %0, %1;" : "=f"(r) : "f"(c)); return r;
+#else
+    return 1.0f / c;
+#endif
 }
+#if IMBA_FAST_RCP
+#define IMBA_ROBUST_TFAR_DEV 1.00000095f /* 1 + 2^-20: one more ulp of slack for the approximate reciprocal */
+#else
+#define IMBA_ROBUST_TFAR_DEV IMBA_ROBUST_TFAR
+#endif
 __device__ __forceinline__ uint32_t sign_extend_s8x4(uint32_t x) {
     uint32_t r; asm("prmt.b32 %0, %1, 0, 0xBA98;" : "=r"(r) : "r"(x)); return r;
 }
@@ -75,7 +90,7 @@ __device__ __forceinline__ uint32_t child_test(uint32_t nx, uint32_t fx, uint32_
     const float t0z = __fmaf_rn(byte_cvt<2, J>(nz), adjz, orgz), t1z = __fmaf_rn(byte_cvt<2, J>(fz), adjz, orgz);
     const float tn = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, tmin));
     const float tf = fminf(fminf(t1x, t1y), fminf(t1z, tbest));
-    if (tn <= tf * IMBA_ROBUST_TFAR) {
+    if (tn <= tf * IMBA_ROBUST_TFAR_DEV) {
         const uint32_t cb = (child_bits4 >> (8 * J)) & 0xffu, bi = (bit_index4 >> (8 * J)) & 0xffu;
         return cb << bi;
     }
@@ -250,7 +265,7 @@ __device__ __forceinline__ uint32_t node_step_coop(const uint4 n0, const uint4 n
         const float t0z = __fmaf_rn(byte_f(nz, j), adjz, orgz), t1z = __fmaf_rn(byte_f(fz, j), adjz, orgz);
         const float tn = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, tmin));
         const float tf = fminf(fminf(t1x, t1y), fminf(t1z, tbest));
-        if (tn <= tf * IMBA_ROBUST_TFAR) {
+        if (tn <= tf * IMBA_ROBUST_TFAR_DEV) {
             const uint32_t cb = (child_bits4 >> (8 * j)) & 0xffu, bi = (bit_index4 >> (8 * j)) & 0xffu;
             contrib = cb << bi;
         }
