@@ -135,3 +135,22 @@ def test_coplanar_rays_are_the_known_hit_or_miss_class():
         p = r["org"].astype(np.float64) + float(h["tmax"]) * d
         lo, hi = np.minimum(np.minimum(p0, p1), p2), np.maximum(np.maximum(p0, p1), p2)
         assert ((p < lo - 1e-3) | (p > hi + 1e-3)).any()                          # the reported point is not on the triangle
+
+
+def test_edge_of_box_ray_is_the_known_hit_or_miss_class():
+    """DESIGN.md section 1, stress run: a ray that crosses the plane of a wall triangle 5e-5 ABOVE its top edge.  The inside
+    test's rounding still accepts the point; the exact leaf box of the reference layout ends at the edge (oracle: miss), the
+    8-bit boxes of the converted tree are a rounding wider (walker and CUDA path: hit).  Found by tools/gpu_parity_stress.py."""
+    from imbatracer_b200 import procedural
+    flat = procedural.still_life_proxy(1.0)
+    rays = np.zeros(1, abi.RAY)
+    rays[0] = ((-2.0397363, 8.315759, 3.6616228), 0.0, (-0.4574975, -0.073693514, 0.886152), np.finfo(np.float32).max)
+    assert refapi.trace_oracle(flat, rays)["tri_id"][0] == -1
+    w = refapi.Bvh8Host(flat).walk(rays)
+    assert w["tri_id"][0] == 0 and abs(float(w["tmax"][0]) - 4.284753) < 1e-5
+    idx = flat.indices.reshape(-1, 4); v = flat.vertices.reshape(-1, 4)[:, :3].astype(np.float64)
+    tri = v[idx[0, :3]]
+    p = rays[0]["org"].astype(np.float64) + float(w["tmax"][0]) * rays[0]["dir"].astype(np.float64)
+    over = p[1] - tri[:, 1].max()
+    assert 0 < over < 1e-4           # outside the triangle's own bounds, by a rounding error of the ray arithmetic
+
