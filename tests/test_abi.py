@@ -83,3 +83,6 @@ def test_traversal_kernel_resource_budget():
     spills = [int(x) for x in re.findall(r"(\d+) bytes spill stores", text)]
     assert regs and max(regs) <= 64, regs
     assert max(spills) == 0, spills
+    # the flat closest-hit / any-hit kernels (no counters) are tuned for 48 registers = 10 resident blocks
+    flat = re.findall(r"Compiling entry function '\S*trace_flat_kernelILi([01])ELb([01])ELb0E\S*'.*?Used (\d+) registers", text, re.S)
+    assert len(flat) == 4 and all(int(r) <= 48 for _, _, r in flat), flat
